@@ -1,0 +1,193 @@
+/*
+ * mcb200.h -- C-ABI of the B200-native Monte Carlo pricing engine (libmcb200.so).
+ *
+ * This is the drop-in boundary for the GBM hot path of amauryrlm/Monte-Carlo-Project-CUDA.
+ * The reference has no FFI layer: its boundary is the set of free functions in
+ * inc/wrappers.cuh plus Simulation::simulate_outer_trajectories (inc/testing.cuh:281).
+ * Every entry point below names the reference interface it replaces (file:line relative
+ * to the reference repo).  Plain pointers and sizes only; no C++/torch types.
+ *
+ * Conventions
+ *   - every function returns an mcb_status; mcb_last_error() gives the message.  The
+ *     library never prints and never calls exit() (the reference does both:
+ *     inc/tool.cuh:92-100, inc/wrappers.cuh:52).
+ *   - there is NO CPU fallback: without a CUDA device mcb_engine_create fails.
+ *   - RNG: stateless Philox4x32-10.  Path p of a run with seed s draws from the cuRAND
+ *     stream curand_init(s, subsequence = p, offset = 0, curandStatePhilox4_32_10_t*) --
+ *     the same call shape as the reference's curand_init(seed, tid, 0, ...) at
+ *     inc/tool.cuh:194.  Step i of a path uses normal i of that stream
+ *     (curand_normal order: even -> s*sin, odd -> s*cos, curand_normal.h:345-360).
+ *   - results are a pure function of (parameters, seed, n_paths): independent of grid
+ *     shape, of threadsPerBlock hints and of the number of GPUs.
+ */
+#ifndef MCB200_H
+#define MCB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCB_VERSION 1
+
+/* Geometry of the deterministic reduction (replaces inc/reduce.cuh + the float atomics). */
+#define MCB_SLOTS 256                   /* accumulation slots per chunk = CTA threads          */
+#define MCB_SEGMENTS 64                 /* double-precision segments per run                  */
+#define MCB_EUROPEAN_PATHS_PER_SLOT 64  /* European / sweep chunk = 16384 paths               */
+#define MCB_BULLET_PATHS_PER_SLOT 4     /* bullet chunk = 1024 paths                          */
+
+/* Byte-compatible with the reference's `struct OptionData` (inc/tool.cuh:13-26, 48 bytes). */
+typedef struct mcb_option_data {
+    float S0, T, K, r, v, B;
+    int P1, P2, N_PATHS, N_PATHS_INNER, N_STEPS;
+    float step;
+} mcb_option_data;
+
+/* Replaces the bare `float` the wrappers return (inc/wrappers.cuh:51-56). */
+typedef struct mcb_result {
+    double price;      /* exp(-rT) * sum / n_paths                       (inc/wrappers.cuh:51) */
+    double std_error;  /* from the sum of squares; the reference has none                      */
+    double sum;        /* undiscounted payoff sum                                              */
+    double sumsq;      /* undiscounted sum of squared payoffs                                  */
+    uint64_t n_paths;
+} mcb_result;
+
+typedef struct mcb_device_info {
+    char name[128];
+    int sm_count;
+    int cc_major, cc_minor;
+    int clock_khz;
+    size_t total_mem;
+} mcb_device_info;
+
+typedef enum mcb_status {
+    MCB_OK = 0,
+    MCB_ERR_INVALID = 1,   /* bad argument                                  */
+    MCB_ERR_CUDA = 2,      /* CUDA runtime error (see mcb_last_error)       */
+    MCB_ERR_NO_DEVICE = 3, /* no usable sm_100 device                       */
+    MCB_ERR_NOMEM = 4
+} mcb_status;
+
+enum { MCB_CALL = 0, MCB_PUT = 1 };
+enum { MCB_DISCOUNT_COMPAT = 0,   /* exp(-rT) for every k, as inc/nmc.cuh:101,268,379 */
+       MCB_DISCOUNT_CORRECT = 1 };/* exp(-r (T - t_{k+1}))                             */
+enum { MCB_HOST = 0, MCB_DEVICE = 1 }; /* where a caller-provided buffer lives */
+
+typedef struct mcb_engine mcb_engine;
+
+/* ---- engine lifetime.  Replaces the per-call cudaMalloc/cudaFree of every wrapper
+ *      (inc/wrappers.cuh:38-55) with a persistent handle owning stream + workspaces. ---- */
+int mcb_engine_create(int device, mcb_engine **out);
+int mcb_engine_destroy(mcb_engine *e);
+const char *mcb_last_error(void);
+int mcb_version(void);
+int mcb_get_device_info(mcb_engine *e, mcb_device_info *out);   /* getDeviceProperty, inc/tool.cuh:56-88 */
+int mcb_synchronize(mcb_engine *e);
+
+/* ---- whole-job, synchronous entry points ------------------------------------------- */
+
+/* European call/put, single step.  Replaces wrapper_gpu_option_vanilla
+ * (inc/wrappers.cuh:33-57) = setup_kernel (inc/tool.cuh:192) +
+ * simulateOptionPriceMultipleBlockGPUwithReduce (inc/trajectories.cuh:54-113) + host
+ * finalise.  n_paths == 0 means opt->N_PATHS.  Reference defaults: seed 1234, MCB_CALL. */
+int mcb_price_european(mcb_engine *e, const mcb_option_data *opt, uint64_t n_paths, uint64_t seed,
+                       int option_type, mcb_result *out);
+
+/* Bullet (barrier-count) option, N_STEPS - Tk steps, restartable from (Ik, Sk, Tk).
+ * Replaces wrapper_gpu_bullet_option and wrapper_gpu_bullet_option_atomic
+ * (inc/wrappers.cuh:59-93, 95-125) = simulateBulletOptionPriceMultipleBlockGPU[atomic]
+ * (inc/trajectories.cuh:115-191, 193-271). */
+int mcb_price_bullet(mcb_engine *e, const mcb_option_data *opt, uint64_t n_paths, uint64_t seed,
+                     int Ik, float Sk, int Tk, mcb_result *out);
+
+/* Full trajectories, path-major: prices[(p-first_path)*N_STEPS + i] = S(t_{i+1}); counts
+ * (nullable) the barrier count after that step.  Replaces
+ * Simulation::simulate_outer_trajectories + its kernel (inc/testing.cuh:281-326, 46-73) and
+ * simulate_outer_trajectories (inc/trajectories.cuh:273-351).  `where` says whether prices /
+ * counts are host or device pointers. */
+int mcb_simulate_trajectories(mcb_engine *e, const mcb_option_data *opt, uint64_t first_path,
+                              uint64_t n_paths, uint64_t seed, float *prices, int *counts, int where);
+
+/* Nested Monte Carlo: F[(p-first_outer)*N_STEPS + k] = discount * mean over N_PATHS_INNER
+ * inner paths started from the outer state (S, I) of path p at step k.  Replaces the three
+ * wrappers wrapper_gpu_bullet_option_nmc_{one_point_one_block,one_kernel,optimal}
+ * (inc/wrappers.cuh:128-206, 209-266, 268-340) and their kernels (inc/nmc.cuh:12-386).
+ * prices / counts (nullable) receive the outer trajectories.  *mean_F (nullable) receives
+ * the wrappers' diagnostic scalar: sum(F) / (n_outer*N_STEPS + 1) (inc/wrappers.cuh:185-189). */
+int mcb_nested_monte_carlo(mcb_engine *e, const mcb_option_data *opt, uint64_t first_outer,
+                           uint64_t n_outer, uint64_t seed_outer, uint64_t seed_inner,
+                           int discount_mode, float *F, float *prices, int *counts, int where,
+                           double *mean_F);
+
+/* Batched strike/vol sweep with common random numbers (BASELINE config 5): out[i] is
+ * bit-identical to mcb_price_european with K = strikes[i], v = vols[i].  New capability. */
+int mcb_price_sweep(mcb_engine *e, const mcb_option_data *opt, const float *strikes, const float *vols,
+                    int n_params, uint64_t n_paths, uint64_t seed, int option_type, mcb_result *out);
+
+/* Deterministic float sum of an array (replaces reduce3..6, inc/reduce.cuh:9-227, as used
+ * by Simulation::test_reduction, inc/testing.cuh:185-235). */
+int mcb_reduce_sum(mcb_engine *e, const float *x, uint64_t n, int where, float *out);
+
+/* European-style pricing from pre-generated normals normals[p*n_steps + i]; payoffs[p].
+ * Replaces simulateOptionPriceGPU / simulateOptionPriceMultipleBlockGPU
+ * (inc/trajectories.cuh:14-52) and the CPU overload (inc/testing.cuh:75-91). */
+int mcb_price_from_normals(mcb_engine *e, const mcb_option_data *opt, const float *normals,
+                           uint64_t n_paths, int n_steps, float *payoffs, int where);
+
+/* ---- sharded, stream-ordered pieces (one process per GPU; no host sync inside) -------
+ * rank g of `world` owns segments [g*64/world, (g+1)*64/world).  The *_segments_async
+ * calls fill d_segments[MCB_SEGMENTS][2] (sum, sumsq; device doubles) with the owned
+ * segments and +0.0 elsewhere, so ONE sum-allreduce (or all-gather) of 1 KiB makes every
+ * rank hold all 64; mcb_combine_segments_async then runs the fixed final tree.  With
+ * world == 1 no collective is needed.  `stream` is a cudaStream_t (NULL = engine stream). */
+int mcb_european_segments_async(mcb_engine *e, const mcb_option_data *opt, uint64_t n_paths,
+                                uint64_t seed, int option_type, int rank, int world,
+                                double *d_segments, void *stream);
+int mcb_bullet_segments_async(mcb_engine *e, const mcb_option_data *opt, uint64_t n_paths,
+                              uint64_t seed, int Ik, float Sk, int Tk, int rank, int world,
+                              double *d_segments, void *stream);
+/* strikes / vols are HOST arrays (n_params floats each); d_segments holds n_params sets of
+ * [MCB_SEGMENTS][2] device doubles. */
+int mcb_sweep_segments_async(mcb_engine *e, const mcb_option_data *opt, const float *strikes,
+                             const float *vols, int n_params, uint64_t n_paths, uint64_t seed,
+                             int option_type, int rank, int world, double *d_segments, void *stream);
+int mcb_combine_segments_async(mcb_engine *e, const double *d_segments, int n_sets, uint64_t n_paths,
+                               float r, float T, mcb_result *d_results, void *stream);
+/* Same as mcb_simulate_trajectories with device pointers, but only enqueues. */
+int mcb_trajectories_async(mcb_engine *e, const mcb_option_data *opt, uint64_t first_path,
+                           uint64_t n_paths, uint64_t seed, float *d_prices, int *d_counts, void *stream);
+int mcb_nested_async(mcb_engine *e, const mcb_option_data *opt, uint64_t first_outer, uint64_t n_outer,
+                     uint64_t seed_outer, uint64_t seed_inner, int discount_mode, float *d_F,
+                     float *d_prices, int *d_counts, void *stream);
+
+/* Number of kernel launches this engine has issued (bench.py's gpu_launches). */
+uint64_t mcb_launch_count(mcb_engine *e);
+
+/* ---- parity hooks (used by tests/ to pin the integer stream and the reduction tree) -- */
+/* words[4*i..] = Philox block `blocks[i]` of subsequence `subsequences[i]` (host arrays). */
+int mcb_philox_blocks(mcb_engine *e, uint64_t seed, const uint64_t *subsequences, const uint64_t *blocks,
+                      uint64_t n, uint32_t *words);
+/* Same words, produced on the device by the cuRAND LIBRARY's curandStatePhilox4_32_10_t
+ * (curand_init(seed, subsequence, 4*block) + curand4): the live oracle of SURVEY.md 8(c). */
+int mcb_curand_blocks(mcb_engine *e, uint64_t seed, const uint64_t *subsequences, const uint64_t *blocks,
+                      uint64_t n, uint32_t *words);
+/* The engine's float normals n0..n0+count-1 of one stream (host array out). */
+int mcb_stream_normals(mcb_engine *e, uint64_t seed, uint64_t subsequence, uint64_t n0, uint64_t count,
+                       float *normals);
+/* Per-path European payoffs (host array, n_paths floats) and per-chunk float partials
+ * (host array, 2 floats per chunk) of paths [0, n_paths). */
+int mcb_european_payoffs(mcb_engine *e, const mcb_option_data *opt, uint64_t first_path, uint64_t n_paths,
+                         uint64_t seed, int option_type, float *payoffs);
+int mcb_european_chunk_partials(mcb_engine *e, const mcb_option_data *opt, uint64_t n_paths, uint64_t seed,
+                                int option_type, float *partials, uint64_t n_chunks);
+int mcb_bullet_payoffs(mcb_engine *e, const mcb_option_data *opt, uint64_t first_path, uint64_t n_paths,
+                       uint64_t seed, int Ik, float Sk, int Tk, float *payoffs);
+/* Last segments [MCB_SEGMENTS][2] computed by a whole-job call (host array of 128 doubles). */
+int mcb_last_segments(mcb_engine *e, double *segments);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCB200_H */

@@ -1,0 +1,860 @@
+// mcb200.cu -- engine + C-ABI (include/mcb200.h) of the B200-native Monte Carlo pricer.
+//
+// Host side of the drop-in boundary: what the reference does inside every wrapper_* of
+// inc/wrappers.cuh (cudaMalloc states/outputs -> setup_kernel -> kernel -> sync -> D2H ->
+// host finalise -> cudaFree) becomes a persistent engine handle with its own stream and
+// grow-only workspaces; parameters travel as kernel arguments (no __constant__ symbol the
+// caller must remember to upload, cf. hello.cu:22); nothing prints, nothing exits.
+// There is deliberately no CPU fallback anywhere in this file.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include <cuda_runtime.h>
+#include <curand_kernel.h>  // device API, used ONLY by the mcb_curand_blocks parity hook
+
+#include "../../include/mcb200.h"
+#include "path_kernels.cuh"
+#include "pricing_kernels.cuh"
+
+using namespace mcb;
+
+static_assert(sizeof(mcb_option_data) == 48, "must match the reference's OptionData (inc/tool.cuh:13-26)");
+static_assert(sizeof(mcb_result) == sizeof(ResultDev), "mcb_result layout");
+static_assert(MCB_SLOTS == kSlots && MCB_SEGMENTS == kSegments, "reduction geometry");
+
+namespace {
+
+thread_local char g_error[512] = "";
+
+int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t err__ = (call);                                                                \
+        if (err__ != cudaSuccess)                                                                  \
+            return fail(MCB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(err__),   \
+                        __FILE__, __LINE__);                                                       \
+    } while (0)
+
+constexpr double kLog2e = 1.4426950408889634074;
+
+template <typename T>
+struct DeviceBuffer {
+    T *ptr = nullptr;
+    size_t cap = 0;  // elements
+    int reserve(size_t n)
+    {
+        if (n <= cap) return MCB_OK;
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        cap = 0;
+        size_t want = n + n / 4 + 64;
+        cudaError_t err = cudaMalloc(&ptr, want * sizeof(T));
+        if (err != cudaSuccess) {
+            cudaGetLastError();
+            return fail(MCB_ERR_NOMEM, "cudaMalloc(%zu bytes) failed: %s", want * sizeof(T), cudaGetErrorString(err));
+        }
+        cap = want;
+        return MCB_OK;
+    }
+    void release()
+    {
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        cap = 0;
+    }
+};
+
+}  // namespace
+
+struct mcb_engine {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaDeviceProp prop{};
+    DeviceBuffer<float2> partials;
+    DeviceBuffer<double> segments;
+    DeviceBuffer<ResultDev> results;
+    DeviceBuffer<unsigned char> scratch;   // hooks / host<->device staging
+    mcb_result *h_results = nullptr;       // pinned
+    size_t h_results_cap = 0;
+    double *h_segments = nullptr;          // pinned, [MCB_SEGMENTS][2] of the last whole-job call
+    uint64_t launches = 0;
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+cudaStream_t pick(mcb_engine *e, void *stream) { return stream ? (cudaStream_t)stream : e->stream; }
+
+int check_common(const mcb_engine *e, const mcb_option_data *o)
+{
+    if (!e) return fail(MCB_ERR_INVALID, "engine is NULL");
+    if (!o) return fail(MCB_ERR_INVALID, "option data is NULL");
+    if (!(o->S0 > 0.0f) || !std::isfinite(o->S0)) return fail(MCB_ERR_INVALID, "S0 must be positive and finite");
+    if (!std::isfinite(o->K)) return fail(MCB_ERR_INVALID, "K must be finite");
+    if (!(o->T > 0.0f) || !std::isfinite(o->T)) return fail(MCB_ERR_INVALID, "T must be positive and finite");
+    if (!(o->v >= 0.0f) || !std::isfinite(o->v)) return fail(MCB_ERR_INVALID, "v (sigma) must be >= 0 and finite");
+    if (!std::isfinite(o->r)) return fail(MCB_ERR_INVALID, "r must be finite");
+    return MCB_OK;
+}
+
+int check_walk(const mcb_option_data *o)
+{
+    if (o->N_STEPS < 1) return fail(MCB_ERR_INVALID, "N_STEPS must be >= 1");
+    if (!(o->step > 0.0f) || !std::isfinite(o->step)) return fail(MCB_ERR_INVALID, "step (dt) must be positive");
+    if (!(o->v > 0.0f)) return fail(MCB_ERR_INVALID, "v (sigma) must be > 0 for multi-step walks");
+    return MCB_OK;
+}
+
+// St = 2^(c0 + c1 z): constants folded in double, rounded once to float.
+EuropeanParams european_params(const mcb_option_data *o, float K, float sigma, uint64_t n_paths_end, uint64_t seed,
+                               uint64_t first_chunk)
+{
+    EuropeanParams p{};
+    const double S0 = o->S0, r = o->r, sig = sigma, T = o->T;
+    p.c0 = (float)(std::log2(S0) + (r - 0.5 * sig * sig) * T * kLog2e);
+    p.c1 = (float)(sig * std::sqrt(T) * kLog2e);
+    p.K = K;
+    p.n_paths = n_paths_end;
+    p.first_chunk = first_chunk;
+    p.keys = make_philox_keys(seed);
+    return p;
+}
+
+struct WalkConsts {
+    float l0, dz, v, lB;
+};
+
+WalkConsts walk_consts(const mcb_option_data *o, double start)
+{
+    WalkConsts w;
+    const double r = o->r, sig = o->v, dt = o->step;
+    w.l0 = (float)std::log2(start);
+    w.dz = (float)((r - 0.5 * sig * sig) * std::sqrt(dt) / sig);
+    w.v = (float)(sig * std::sqrt(dt) * kLog2e);
+    w.lB = o->B > 0.0f ? (float)std::log2((double)o->B) : -INFINITY;
+    return w;
+}
+
+void segment_span(int rank, int world, uint64_t n_chunks, int *seg_lo, int *seg_hi, uint64_t *chunk_lo,
+                  uint64_t *chunk_hi)
+{
+    *seg_lo = (int)(((int64_t)rank * MCB_SEGMENTS) / world);
+    *seg_hi = (int)(((int64_t)(rank + 1) * MCB_SEGMENTS) / world);
+    *chunk_lo = (n_chunks * (uint64_t)*seg_lo) / MCB_SEGMENTS;
+    *chunk_hi = (n_chunks * (uint64_t)*seg_hi) / MCB_SEGMENTS;
+}
+
+int check_shard(int rank, int world)
+{
+    if (world < 1 || rank < 0 || rank >= world) return fail(MCB_ERR_INVALID, "bad rank/world %d/%d", rank, world);
+    return MCB_OK;
+}
+
+template <int PPS>
+int launch_european(mcb_engine *e, const EuropeanParams &prm, int option_type, uint64_t n_ctas, float2 *partials,
+                    float *payoffs, uint64_t payoffs_first, cudaStream_t st)
+{
+    if (n_ctas == 0) return MCB_OK;
+    if (n_ctas > 0x7fffffffull) return fail(MCB_ERR_INVALID, "too many chunks for one launch");
+    if (option_type == MCB_PUT)
+        european_kernel<kPut, PPS><<<(unsigned)n_ctas, kSlots, 0, st>>>(prm, partials, payoffs, payoffs_first);
+    else
+        european_kernel<kCall, PPS><<<(unsigned)n_ctas, kSlots, 0, st>>>(prm, partials, payoffs, payoffs_first);
+    e->launches++;
+    CU(cudaGetLastError());
+    return MCB_OK;
+}
+
+int launch_segments(mcb_engine *e, const float2 *partials, uint64_t stride, uint64_t first_chunk, uint64_t n_chunks,
+                    int seg_lo, int seg_hi, int n_sets, double *d_segments, cudaStream_t st)
+{
+    segment_kernel<<<dim3(MCB_SEGMENTS, (unsigned)n_sets), kSlots, 0, st>>>(partials, stride, first_chunk, n_chunks,
+                                                                           seg_lo, seg_hi, d_segments);
+    e->launches++;
+    CU(cudaGetLastError());
+    return MCB_OK;
+}
+
+int reserve_results(mcb_engine *e, size_t n)
+{
+    int rc = e->results.reserve(n);
+    if (rc) return rc;
+    if (n > e->h_results_cap) {
+        if (e->h_results) cudaFreeHost(e->h_results);
+        e->h_results = nullptr;
+        e->h_results_cap = 0;
+        CU(cudaMallocHost(&e->h_results, (n + 16) * sizeof(mcb_result)));
+        e->h_results_cap = n + 16;
+    }
+    return MCB_OK;
+}
+
+constexpr uint64_t kEuropeanChunk = (uint64_t)MCB_SLOTS * MCB_EUROPEAN_PATHS_PER_SLOT;
+constexpr uint64_t kBulletChunk = (uint64_t)MCB_SLOTS * MCB_BULLET_PATHS_PER_SLOT;
+
+uint64_t resolve_paths(const mcb_option_data *o, uint64_t n_paths)
+{
+    return n_paths ? n_paths : (o->N_PATHS > 0 ? (uint64_t)o->N_PATHS : 0);
+}
+
+__global__ void curand_blocks_kernel(uint64_t seed, const uint64_t *__restrict__ subseq,
+                                     const uint64_t *__restrict__ block, uint64_t n, uint4 *__restrict__ out)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    curandStatePhilox4_32_10_t s;
+    curand_init(seed, subseq[i], 4ull * block[i], &s);
+    out[i] = curand4(&s);
+}
+
+}  // namespace
+
+// ============================================================================================
+extern "C" {
+
+const char *mcb_last_error(void) { return g_error; }
+int mcb_version(void) { return MCB_VERSION; }
+
+int mcb_engine_create(int device, mcb_engine **out)
+{
+    if (!out) return fail(MCB_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t err = cudaGetDeviceCount(&count);
+    if (err != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(MCB_ERR_NO_DEVICE, "no CUDA device: %s (this engine has no CPU fallback)",
+                    err == cudaSuccess ? "device count is 0" : cudaGetErrorString(err));
+    }
+    if (device < 0 || device >= count) return fail(MCB_ERR_INVALID, "device %d out of range [0,%d)", device, count);
+    mcb_engine *e = new (std::nothrow) mcb_engine();
+    if (!e) return fail(MCB_ERR_NOMEM, "out of host memory");
+    e->device = device;
+    DeviceGuard g(device);
+    if (!g.ok) {
+        delete e;
+        return fail(MCB_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+    }
+    err = cudaGetDeviceProperties(&e->prop, device);
+    if (err == cudaSuccess && e->prop.major != 10) {
+        int major = e->prop.major, minor = e->prop.minor;
+        delete e;
+        return fail(MCB_ERR_NO_DEVICE, "device %d is sm_%d%d; this library carries sm_100a code only", device, major,
+                    minor);
+    }
+    if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
+    if (err == cudaSuccess) err = cudaMallocHost(&e->h_segments, sizeof(double) * 2 * MCB_SEGMENTS);
+    if (err != cudaSuccess) {
+        int rc = fail(MCB_ERR_CUDA, "engine setup failed: %s", cudaGetErrorString(err));
+        mcb_engine_destroy(e);
+        return rc;
+    }
+    memset(e->h_segments, 0, sizeof(double) * 2 * MCB_SEGMENTS);
+    if (e->segments.reserve(2 * MCB_SEGMENTS) || reserve_results(e, 1)) {
+        mcb_engine_destroy(e);
+        return MCB_ERR_NOMEM;
+    }
+    *out = e;
+    return MCB_OK;
+}
+
+int mcb_engine_destroy(mcb_engine *e)
+{
+    if (!e) return MCB_OK;
+    DeviceGuard g(e->device);
+    if (e->stream) {
+        cudaStreamSynchronize(e->stream);
+        cudaStreamDestroy(e->stream);
+    }
+    e->partials.release();
+    e->segments.release();
+    e->results.release();
+    e->scratch.release();
+    if (e->h_results) cudaFreeHost(e->h_results);
+    if (e->h_segments) cudaFreeHost(e->h_segments);
+    delete e;
+    return MCB_OK;
+}
+
+int mcb_get_device_info(mcb_engine *e, mcb_device_info *out)
+{
+    if (!e || !out) return fail(MCB_ERR_INVALID, "NULL argument");
+    memset(out, 0, sizeof(*out));
+    strncpy(out->name, e->prop.name, sizeof(out->name) - 1);
+    out->sm_count = e->prop.multiProcessorCount;
+    out->cc_major = e->prop.major;
+    out->cc_minor = e->prop.minor;
+    int khz = 0;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, e->device);
+    out->clock_khz = khz;
+    out->total_mem = e->prop.totalGlobalMem;
+    return MCB_OK;
+}
+
+int mcb_synchronize(mcb_engine *e)
+{
+    if (!e) return fail(MCB_ERR_INVALID, "engine is NULL");
+    DeviceGuard g(e->device);
+    CU(cudaStreamSynchronize(e->stream));
+    return MCB_OK;
+}
+
+uint64_t mcb_launch_count(mcb_engine *e) { return e ? e->launches : 0; }
+
+// -------------------------------------------------------------------------------- European
+int mcb_european_segments_async(mcb_engine *e, const mcb_option_data *opt, uint64_t n_paths, uint64_t seed,
+                                int option_type, int rank, int world, double *d_segments, void *stream)
+{
+    int rc = check_common(e, opt);
+    if (rc) return rc;
+    if ((rc = check_shard(rank, world))) return rc;
+    n_paths = resolve_paths(opt, n_paths);
+    if (n_paths == 0) return fail(MCB_ERR_INVALID, "n_paths must be > 0");
+    if (option_type != MCB_CALL && option_type != MCB_PUT) return fail(MCB_ERR_INVALID, "bad option_type");
+    if (!d_segments) return fail(MCB_ERR_INVALID, "d_segments is NULL");
+    DeviceGuard g(e->device);
+    cudaStream_t st = pick(e, stream);
+    const uint64_t n_chunks = (n_paths + kEuropeanChunk - 1) / kEuropeanChunk;
+    int seg_lo, seg_hi;
+    uint64_t c_lo, c_hi;
+    segment_span(rank, world, n_chunks, &seg_lo, &seg_hi, &c_lo, &c_hi);
+    if ((rc = e->partials.reserve((size_t)(c_hi - c_lo) + 1))) return rc;
+    const EuropeanParams prm = european_params(opt, opt->K, opt->v, n_paths, seed, c_lo);
+    if ((rc = launch_european<MCB_EUROPEAN_PATHS_PER_SLOT>(e, prm, option_type, c_hi - c_lo, e->partials.ptr, nullptr,
+                                                           0, st)))
+        return rc;
+    return launch_segments(e, e->partials.ptr, 0, c_lo, n_chunks, seg_lo, seg_hi, 1, d_segments, st);
+}
+
+int mcb_combine_segments_async(mcb_engine *e, const double *d_segments, int n_sets, uint64_t n_paths, float r, float T,
+                               mcb_result *d_results, void *stream)
+{
+    if (!e || !d_segments || !d_results) return fail(MCB_ERR_INVALID, "NULL argument");
+    if (n_sets < 1 || n_paths == 0) return fail(MCB_ERR_INVALID, "n_sets and n_paths must be positive");
+    DeviceGuard g(e->device);
+    const double discount = std::exp(-(double)r * (double)T);
+    combine_kernel<<<(unsigned)n_sets, 32, 0, pick(e, stream)>>>(d_segments, n_paths, discount,
+                                                                 reinterpret_cast<ResultDev *>(d_results));
+    e->launches++;
+    CU(cudaGetLastError());
+    return MCB_OK;
+}
+
+static int finish_whole_job(mcb_engine *e, int n_sets, uint64_t n_paths, float r, float T, mcb_result *out)
+{
+    int rc = reserve_results(e, (size_t)n_sets);
+    if (rc) return rc;
+    if ((rc = mcb_combine_segments_async(e, e->segments.ptr, n_sets, n_paths, r, T,
+                                         reinterpret_cast<mcb_result *>(e->results.ptr), nullptr)))
+        return rc;
+    CU(cudaMemcpyAsync(e->h_results, e->results.ptr, sizeof(mcb_result) * (size_t)n_sets, cudaMemcpyDeviceToHost,
+                       e->stream));
+    CU(cudaMemcpyAsync(e->h_segments, e->segments.ptr, sizeof(double) * 2 * MCB_SEGMENTS, cudaMemcpyDeviceToHost,
+                       e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    memcpy(out, e->h_results, sizeof(mcb_result) * (size_t)n_sets);
+    return MCB_OK;
+}
+
+int mcb_price_european(mcb_engine *e, const mcb_option_data *opt, uint64_t n_paths, uint64_t seed, int option_type,
+                       mcb_result *out)
+{
+    if (!out) return fail(MCB_ERR_INVALID, "out is NULL");
+    int rc = check_common(e, opt);
+    if (rc) return rc;
+    DeviceGuard g(e->device);
+    n_paths = resolve_paths(opt, n_paths);
+    if ((rc = mcb_european_segments_async(e, opt, n_paths, seed, option_type, 0, 1, e->segments.ptr, nullptr)))
+        return rc;
+    return finish_whole_job(e, 1, n_paths, opt->r, opt->T, out);
+}
+
+// ---------------------------------------------------------------------------------- bullet
+static int bullet_params(const mcb_option_data *opt, uint64_t n_paths_end, uint64_t seed, int Ik, float Sk, int Tk,
+                         uint64_t first_chunk, WalkParams *out)
+{
+    int rc = check_walk(opt);
+    if (rc) return rc;
+    if (Tk < 0 || Tk > opt->N_STEPS) return fail(MCB_ERR_INVALID, "Tk must be in [0, N_STEPS]");
+    if (Sk < 0.0f || !std::isfinite(Sk)) return fail(MCB_ERR_INVALID, "Sk must be >= 0 and finite");
+    // Sk == 0 means "start from S0" exactly as inc/trajectories.cuh:141
+    const WalkConsts w = walk_consts(opt, Sk == 0.0f ? (double)opt->S0 : (double)Sk);
+    WalkParams p{};
+    p.l0 = w.l0; p.dz = w.dz; p.v = w.v; p.lB = w.lB;
+    p.K = opt->K; p.P1 = opt->P1; p.P2 = opt->P2;
+    p.n_steps = opt->N_STEPS - Tk;
+    p.count0 = Ik;
+    p.n_paths = n_paths_end;
+    p.first_chunk = first_chunk;
+    p.keys = make_philox_keys(seed);
+    *out = p;
+    return MCB_OK;
+}
+
+int mcb_bullet_segments_async(mcb_engine *e, const mcb_option_data *opt, uint64_t n_paths, uint64_t seed, int Ik,
+                              float Sk, int Tk, int rank, int world, double *d_segments, void *stream)
+{
+    int rc = check_common(e, opt);
+    if (rc) return rc;
+    if ((rc = check_shard(rank, world))) return rc;
+    n_paths = resolve_paths(opt, n_paths);
+    if (n_paths == 0) return fail(MCB_ERR_INVALID, "n_paths must be > 0");
+    if (!d_segments) return fail(MCB_ERR_INVALID, "d_segments is NULL");
+    DeviceGuard g(e->device);
+    cudaStream_t st = pick(e, stream);
+    const uint64_t n_chunks = (n_paths + kBulletChunk - 1) / kBulletChunk;
+    int seg_lo, seg_hi;
+    uint64_t c_lo, c_hi;
+    segment_span(rank, world, n_chunks, &seg_lo, &seg_hi, &c_lo, &c_hi);
+    if (c_hi - c_lo > 0x7fffffffull) return fail(MCB_ERR_INVALID, "too many chunks for one launch");
+    if ((rc = e->partials.reserve((size_t)(c_hi - c_lo) + 1))) return rc;
+    WalkParams prm;
+    if ((rc = bullet_params(opt, n_paths, seed, Ik, Sk, Tk, c_lo, &prm))) return rc;
+    if (c_hi > c_lo) {
+        bullet_kernel<MCB_BULLET_PATHS_PER_SLOT><<<(unsigned)(c_hi - c_lo), kSlots, 0, st>>>(prm, e->partials.ptr,
+                                                                                             nullptr, 0);
+        e->launches++;
+        CU(cudaGetLastError());
+    }
+    return launch_segments(e, e->partials.ptr, 0, c_lo, n_chunks, seg_lo, seg_hi, 1, d_segments, st);
+}
+
+int mcb_price_bullet(mcb_engine *e, const mcb_option_data *opt, uint64_t n_paths, uint64_t seed, int Ik, float Sk,
+                     int Tk, mcb_result *out)
+{
+    if (!out) return fail(MCB_ERR_INVALID, "out is NULL");
+    int rc = check_common(e, opt);
+    if (rc) return rc;
+    DeviceGuard g(e->device);
+    n_paths = resolve_paths(opt, n_paths);
+    if ((rc = mcb_bullet_segments_async(e, opt, n_paths, seed, Ik, Sk, Tk, 0, 1, e->segments.ptr, nullptr))) return rc;
+    return finish_whole_job(e, 1, n_paths, opt->r, opt->T, out);
+}
+
+// ------------------------------------------------------------------------------------ sweep
+int mcb_sweep_segments_async(mcb_engine *e, const mcb_option_data *opt, const float *strikes, const float *vols,
+                             int n_params, uint64_t n_paths, uint64_t seed, int option_type, int rank, int world,
+                             double *d_segments, void *stream)
+{
+    int rc = check_common(e, opt);
+    if (rc) return rc;
+    if ((rc = check_shard(rank, world))) return rc;
+    if (!strikes || !vols || n_params < 1) return fail(MCB_ERR_INVALID, "bad parameter arrays");
+    n_paths = resolve_paths(opt, n_paths);
+    if (n_paths == 0) return fail(MCB_ERR_INVALID, "n_paths must be > 0");
+    if (option_type != MCB_CALL && option_type != MCB_PUT) return fail(MCB_ERR_INVALID, "bad option_type");
+    if (!d_segments) return fail(MCB_ERR_INVALID, "d_segments is NULL");
+    for (int i = 0; i < n_params; ++i)
+        if (!std::isfinite(strikes[i]) || !(vols[i] >= 0.0f) || !std::isfinite(vols[i]))
+            return fail(MCB_ERR_INVALID, "parameter set %d is not finite / has negative vol", i);
+    DeviceGuard g(e->device);
+    cudaStream_t st = pick(e, stream);
+    const uint64_t n_chunks = (n_paths + kEuropeanChunk - 1) / kEuropeanChunk;
+    int seg_lo, seg_hi;
+    uint64_t c_lo, c_hi;
+    segment_span(rank, world, n_chunks, &seg_lo, &seg_hi, &c_lo, &c_hi);
+    const uint64_t local = c_hi - c_lo;
+    // Parameter sets are priced in groups so the partials workspace stays bounded (<= 64 MiB).
+    uint64_t group = local ? (uint64_t)(8u << 20) / (local ? local : 1) : (uint64_t)n_params;
+    if (group < 1) group = 1;
+    if (group > (uint64_t)n_params) group = (uint64_t)n_params;
+    if ((rc = e->partials.reserve((size_t)(group * (local + 1))))) return rc;
+    for (uint64_t i0 = 0; i0 < (uint64_t)n_params; i0 += group) {
+        const uint64_t cnt = (uint64_t)n_params - i0 < group ? (uint64_t)n_params - i0 : group;
+        for (uint64_t j = 0; j < cnt; ++j) {
+            const EuropeanParams prm = european_params(opt, strikes[i0 + j], vols[i0 + j], n_paths, seed, c_lo);
+            if ((rc = launch_european<MCB_EUROPEAN_PATHS_PER_SLOT>(e, prm, option_type, local,
+                                                                   e->partials.ptr + j * (local + 1), nullptr, 0, st)))
+                return rc;
+        }
+        if ((rc = launch_segments(e, e->partials.ptr, local + 1, c_lo, n_chunks, seg_lo, seg_hi, (int)cnt,
+                                  d_segments + i0 * 2 * MCB_SEGMENTS, st)))
+            return rc;
+    }
+    return MCB_OK;
+}
+
+int mcb_price_sweep(mcb_engine *e, const mcb_option_data *opt, const float *strikes, const float *vols, int n_params,
+                    uint64_t n_paths, uint64_t seed, int option_type, mcb_result *out)
+{
+    if (!out) return fail(MCB_ERR_INVALID, "out is NULL");
+    int rc = check_common(e, opt);
+    if (rc) return rc;
+    if (n_params < 1) return fail(MCB_ERR_INVALID, "n_params must be >= 1");
+    DeviceGuard g(e->device);
+    n_paths = resolve_paths(opt, n_paths);
+    if ((rc = e->segments.reserve((size_t)n_params * 2 * MCB_SEGMENTS))) return rc;
+    if ((rc = mcb_sweep_segments_async(e, opt, strikes, vols, n_params, n_paths, seed, option_type, 0, 1,
+                                       e->segments.ptr, nullptr)))
+        return rc;
+    return finish_whole_job(e, n_params, n_paths, opt->r, opt->T, out);
+}
+
+// ------------------------------------------------------------------------------ trajectories
+int mcb_trajectories_async(mcb_engine *e, const mcb_option_data *opt, uint64_t first_path, uint64_t n_paths,
+                           uint64_t seed, float *d_prices, int *d_counts, void *stream)
+{
+    int rc = check_common(e, opt);
+    if (rc) return rc;
+    if ((rc = check_walk(opt))) return rc;
+    if (!d_prices) return fail(MCB_ERR_INVALID, "prices is NULL");
+    if (n_paths == 0) return MCB_OK;
+    DeviceGuard g(e->device);
+    const WalkConsts w = walk_consts(opt, (double)opt->S0);
+    PathParams prm{};
+    prm.l0 = w.l0; prm.dz = w.dz; prm.v = w.v; prm.lB = w.lB;
+    prm.n_steps = opt->N_STEPS;
+    prm.first_path = first_path;
+    prm.n_paths = n_paths;
+    prm.keys = make_philox_keys(seed);
+    const uint64_t ctas = (n_paths + (uint64_t)kPathWarps * 32 - 1) / ((uint64_t)kPathWarps * 32);
+    if (ctas > 0x7fffffffull) return fail(MCB_ERR_INVALID, "too many paths for one launch");
+    const bool vec = (opt->N_STEPS % 4 == 0) && ((uintptr_t)d_prices % 16 == 0) &&
+                     (!d_counts || (uintptr_t)d_counts % 16 == 0);
+    cudaStream_t st = pick(e, stream);
+    if (vec && d_counts)
+        trajectory_kernel<true, true><<<(unsigned)ctas, kPathWarps * 32, 0, st>>>(prm, d_prices, d_counts);
+    else if (vec)
+        trajectory_kernel<true, false><<<(unsigned)ctas, kPathWarps * 32, 0, st>>>(prm, d_prices, nullptr);
+    else if (d_counts)
+        trajectory_kernel<false, true><<<(unsigned)ctas, kPathWarps * 32, 0, st>>>(prm, d_prices, d_counts);
+    else
+        trajectory_kernel<false, false><<<(unsigned)ctas, kPathWarps * 32, 0, st>>>(prm, d_prices, nullptr);
+    e->launches++;
+    CU(cudaGetLastError());
+    return MCB_OK;
+}
+
+int mcb_simulate_trajectories(mcb_engine *e, const mcb_option_data *opt, uint64_t first_path, uint64_t n_paths,
+                              uint64_t seed, float *prices, int *counts, int where)
+{
+    int rc = check_common(e, opt);
+    if (rc) return rc;
+    if ((rc = check_walk(opt))) return rc;
+    if (!prices) return fail(MCB_ERR_INVALID, "prices is NULL");
+    DeviceGuard g(e->device);
+    if (where == MCB_DEVICE) {
+        if ((rc = mcb_trajectories_async(e, opt, first_path, n_paths, seed, prices, counts, nullptr))) return rc;
+        CU(cudaStreamSynchronize(e->stream));
+        return MCB_OK;
+    }
+    if (where != MCB_HOST) return fail(MCB_ERR_INVALID, "bad `where`");
+    const size_t n = (size_t)n_paths * (size_t)opt->N_STEPS;
+    if (n == 0) return MCB_OK;
+    float *dp = nullptr;
+    int *dc = nullptr;
+    cudaError_t err = cudaMalloc(&dp, n * sizeof(float));
+    if (err == cudaSuccess && counts) err = cudaMalloc(&dc, n * sizeof(int));
+    if (err != cudaSuccess) {
+        cudaGetLastError();
+        if (dp) cudaFree(dp);
+        return fail(MCB_ERR_NOMEM, "cudaMalloc for %zu trajectory points failed: %s", n, cudaGetErrorString(err));
+    }
+    rc = mcb_trajectories_async(e, opt, first_path, n_paths, seed, dp, dc, nullptr);
+    if (rc == MCB_OK) {
+        err = cudaMemcpyAsync(prices, dp, n * sizeof(float), cudaMemcpyDeviceToHost, e->stream);
+        if (err == cudaSuccess && counts)
+            err = cudaMemcpyAsync(counts, dc, n * sizeof(int), cudaMemcpyDeviceToHost, e->stream);
+        if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+        if (err != cudaSuccess) rc = fail(MCB_ERR_CUDA, "trajectory copy-back failed: %s", cudaGetErrorString(err));
+    }
+    cudaFree(dp);
+    if (dc) cudaFree(dc);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------- nested MC
+int mcb_nested_async(mcb_engine *e, const mcb_option_data *opt, uint64_t first_outer, uint64_t n_outer,
+                     uint64_t seed_outer, uint64_t seed_inner, int discount_mode, float *d_F, float *d_prices,
+                     int *d_counts, void *stream)
+{
+    int rc = check_common(e, opt);
+    if (rc) return rc;
+    if ((rc = check_walk(opt))) return rc;
+    if (!d_F) return fail(MCB_ERR_INVALID, "F is NULL");
+    if (opt->N_PATHS_INNER < 1) return fail(MCB_ERR_INVALID, "N_PATHS_INNER must be >= 1");
+    if (discount_mode != MCB_DISCOUNT_COMPAT && discount_mode != MCB_DISCOUNT_CORRECT)
+        return fail(MCB_ERR_INVALID, "bad discount_mode");
+    if (n_outer == 0) return MCB_OK;
+    if (n_outer > 0x7fffffffull) return fail(MCB_ERR_INVALID, "too many outer paths for one launch");
+    DeviceGuard g(e->device);
+    const WalkConsts w = walk_consts(opt, (double)opt->S0);
+    NestedParams prm{};
+    prm.l0 = w.l0; prm.dz = w.dz; prm.v = w.v; prm.lB = w.lB;
+    prm.K = opt->K; prm.P1 = opt->P1; prm.P2 = opt->P2;
+    prm.n_steps = opt->N_STEPS;
+    prm.n_inner = opt->N_PATHS_INNER;
+    prm.discount_mode = discount_mode;
+    prm.r = opt->r; prm.T = opt->T; prm.dt = opt->step;
+    prm.first_outer = first_outer;
+    prm.keys_outer = make_philox_keys(seed_outer);
+    prm.keys_inner = make_philox_keys(seed_inner);
+    nested_kernel<<<(unsigned)n_outer, kSlots, 0, pick(e, stream)>>>(prm, d_F, d_prices, d_counts);
+    e->launches++;
+    CU(cudaGetLastError());
+    return MCB_OK;
+}
+
+int mcb_nested_monte_carlo(mcb_engine *e, const mcb_option_data *opt, uint64_t first_outer, uint64_t n_outer,
+                           uint64_t seed_outer, uint64_t seed_inner, int discount_mode, float *F, float *prices,
+                           int *counts, int where, double *mean_F)
+{
+    int rc = check_common(e, opt);
+    if (rc) return rc;
+    if ((rc = check_walk(opt))) return rc;
+    if (!F) return fail(MCB_ERR_INVALID, "F is NULL");
+    if (where != MCB_HOST && where != MCB_DEVICE) return fail(MCB_ERR_INVALID, "bad `where`");
+    DeviceGuard g(e->device);
+    const size_t n = (size_t)n_outer * (size_t)opt->N_STEPS;
+    if (n == 0) {
+        if (mean_F) *mean_F = 0.0;
+        return MCB_OK;
+    }
+    float *dF = F, *dP = prices;
+    int *dC = counts;
+    std::vector<float> hostF;
+    if (where == MCB_HOST) {
+        const size_t bytes = n * sizeof(float) * (prices ? 2 : 1) + (counts ? n * sizeof(int) : 0);
+        if ((rc = e->scratch.reserve(bytes))) return rc;
+        dF = reinterpret_cast<float *>(e->scratch.ptr);
+        dP = prices ? dF + n : nullptr;
+        dC = counts ? reinterpret_cast<int *>(dF + (prices ? 2 * n : n)) : nullptr;
+    }
+    if ((rc = mcb_nested_async(e, opt, first_outer, n_outer, seed_outer, seed_inner, discount_mode, dF, dP, dC,
+                               nullptr)))
+        return rc;
+    const float *sumsrc = nullptr;
+    if (where == MCB_HOST) {
+        CU(cudaMemcpyAsync(F, dF, n * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+        if (prices) CU(cudaMemcpyAsync(prices, dP, n * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+        if (counts) CU(cudaMemcpyAsync(counts, dC, n * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaStreamSynchronize(e->stream));
+        sumsrc = F;
+    } else {
+        if (mean_F) {
+            hostF.resize(n);
+            CU(cudaMemcpyAsync(hostF.data(), dF, n * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+        }
+        CU(cudaStreamSynchronize(e->stream));
+        sumsrc = hostF.data();
+    }
+    if (mean_F) {
+        // the wrappers' diagnostic scalar: mean over N*steps + 1 slots (inc/wrappers.cuh:134,185-189)
+        double s = 0.0;
+        for (size_t i = 0; i < n; ++i) s += (double)sumsrc[i];
+        *mean_F = s / (double)(n + 1);
+    }
+    return MCB_OK;
+}
+
+// ------------------------------------------------------------------- reduce / pre-generated
+int mcb_reduce_sum(mcb_engine *e, const float *x, uint64_t n, int where, float *out)
+{
+    if (!e || !out || (!x && n)) return fail(MCB_ERR_INVALID, "NULL argument");
+    if (where != MCB_HOST && where != MCB_DEVICE) return fail(MCB_ERR_INVALID, "bad `where`");
+    DeviceGuard g(e->device);
+    int rc;
+    const float *dx = x;
+    if (where == MCB_HOST) {
+        if ((rc = e->scratch.reserve((size_t)n * sizeof(float) + 16))) return rc;
+        if (n) CU(cudaMemcpyAsync(e->scratch.ptr, x, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+        dx = reinterpret_cast<const float *>(e->scratch.ptr);
+    }
+    if ((rc = reserve_results(e, 1))) return rc;
+    float *d_out = reinterpret_cast<float *>(e->results.ptr);
+    reduce_sum_kernel<<<1, kSlots, 0, e->stream>>>(dx, n, d_out);
+    e->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(e->h_results, d_out, sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    memcpy(out, e->h_results, sizeof(float));
+    return MCB_OK;
+}
+
+int mcb_price_from_normals(mcb_engine *e, const mcb_option_data *opt, const float *normals, uint64_t n_paths,
+                           int n_steps, float *payoffs, int where)
+{
+    int rc = check_common(e, opt);
+    if (rc) return rc;
+    if (!normals || !payoffs) return fail(MCB_ERR_INVALID, "NULL argument");
+    if (n_steps < 1 || !(opt->step > 0.0f) || !(opt->v > 0.0f)) return fail(MCB_ERR_INVALID, "bad steps/dt/sigma");
+    if (where != MCB_HOST && where != MCB_DEVICE) return fail(MCB_ERR_INVALID, "bad `where`");
+    if (n_paths == 0) return MCB_OK;
+    DeviceGuard g(e->device);
+    const WalkConsts w = walk_consts(opt, (double)opt->S0);
+    const size_t nz = (size_t)n_paths * (size_t)n_steps;
+    const float *dz = normals;
+    float *dp = payoffs;
+    if (where == MCB_HOST) {
+        if ((rc = e->scratch.reserve((nz + (size_t)n_paths) * sizeof(float)))) return rc;
+        float *base = reinterpret_cast<float *>(e->scratch.ptr);
+        CU(cudaMemcpyAsync(base, normals, nz * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+        dz = base;
+        dp = base + nz;
+    }
+    const uint64_t ctas = (n_paths + kSlots - 1) / kSlots;
+    pregen_kernel<<<(unsigned)ctas, kSlots, 0, e->stream>>>(dz, n_paths, n_steps, w.l0, w.dz, w.v, opt->K, dp);
+    e->launches++;
+    CU(cudaGetLastError());
+    if (where == MCB_HOST)
+        CU(cudaMemcpyAsync(payoffs, dp, (size_t)n_paths * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return MCB_OK;
+}
+
+// ------------------------------------------------------------------------------ parity hooks
+static int blocks_hook(mcb_engine *e, uint64_t seed, const uint64_t *subsequences, const uint64_t *blocks, uint64_t n,
+                       uint32_t *words, bool library)
+{
+    if (!e || !subsequences || !blocks || !words) return fail(MCB_ERR_INVALID, "NULL argument");
+    if (n == 0) return MCB_OK;
+    DeviceGuard g(e->device);
+    int rc;
+    const size_t in_bytes = (size_t)n * sizeof(uint64_t);
+    if ((rc = e->scratch.reserve(2 * in_bytes + (size_t)n * 16))) return rc;
+    uint64_t *d_sub = reinterpret_cast<uint64_t *>(e->scratch.ptr);
+    uint64_t *d_blk = d_sub + n;
+    uint4 *d_out = reinterpret_cast<uint4 *>(d_blk + n);
+    CU(cudaMemcpyAsync(d_sub, subsequences, in_bytes, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(d_blk, blocks, in_bytes, cudaMemcpyHostToDevice, e->stream));
+    const unsigned ctas = (unsigned)((n + 127) / 128);
+    if (library)
+        curand_blocks_kernel<<<ctas, 128, 0, e->stream>>>(seed, d_sub, d_blk, n, d_out);
+    else
+        philox_blocks_kernel<<<ctas, 128, 0, e->stream>>>(make_philox_keys(seed), d_sub, d_blk, n, d_out);
+    e->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(words, d_out, (size_t)n * 16, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return MCB_OK;
+}
+
+int mcb_philox_blocks(mcb_engine *e, uint64_t seed, const uint64_t *subsequences, const uint64_t *blocks, uint64_t n,
+                      uint32_t *words)
+{
+    return blocks_hook(e, seed, subsequences, blocks, n, words, false);
+}
+
+int mcb_curand_blocks(mcb_engine *e, uint64_t seed, const uint64_t *subsequences, const uint64_t *blocks, uint64_t n,
+                      uint32_t *words)
+{
+    return blocks_hook(e, seed, subsequences, blocks, n, words, true);
+}
+
+int mcb_stream_normals(mcb_engine *e, uint64_t seed, uint64_t subsequence, uint64_t n0, uint64_t count, float *normals)
+{
+    if (!e || !normals) return fail(MCB_ERR_INVALID, "NULL argument");
+    if (count == 0) return MCB_OK;
+    DeviceGuard g(e->device);
+    int rc;
+    if ((rc = e->scratch.reserve((size_t)count * sizeof(float)))) return rc;
+    float *d = reinterpret_cast<float *>(e->scratch.ptr);
+    stream_normals_kernel<<<(unsigned)((count + 127) / 128), 128, 0, e->stream>>>(make_philox_keys(seed), subsequence,
+                                                                               n0, count, d);
+    e->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(normals, d, (size_t)count * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return MCB_OK;
+}
+
+int mcb_european_payoffs(mcb_engine *e, const mcb_option_data *opt, uint64_t first_path, uint64_t n_paths,
+                         uint64_t seed, int option_type, float *payoffs)
+{
+    int rc = check_common(e, opt);
+    if (rc) return rc;
+    if (!payoffs) return fail(MCB_ERR_INVALID, "payoffs is NULL");
+    if (n_paths == 0) return MCB_OK;
+    DeviceGuard g(e->device);
+    const uint64_t c_lo = first_path / kEuropeanChunk;
+    const uint64_t c_hi = (first_path + n_paths + kEuropeanChunk - 1) / kEuropeanChunk;
+    if ((rc = e->partials.reserve((size_t)(c_hi - c_lo) + 1))) return rc;
+    if ((rc = e->scratch.reserve((size_t)n_paths * sizeof(float)))) return rc;
+    float *d = reinterpret_cast<float *>(e->scratch.ptr);
+    const EuropeanParams prm = european_params(opt, opt->K, opt->v, first_path + n_paths, seed, c_lo);
+    if ((rc = launch_european<MCB_EUROPEAN_PATHS_PER_SLOT>(e, prm, option_type, c_hi - c_lo, e->partials.ptr, d,
+                                                           first_path, e->stream)))
+        return rc;
+    CU(cudaMemcpyAsync(payoffs, d, (size_t)n_paths * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return MCB_OK;
+}
+
+int mcb_european_chunk_partials(mcb_engine *e, const mcb_option_data *opt, uint64_t n_paths, uint64_t seed,
+                                int option_type, float *partials, uint64_t n_chunks)
+{
+    int rc = check_common(e, opt);
+    if (rc) return rc;
+    if (!partials) return fail(MCB_ERR_INVALID, "partials is NULL");
+    n_paths = resolve_paths(opt, n_paths);
+    const uint64_t need = (n_paths + kEuropeanChunk - 1) / kEuropeanChunk;
+    if (n_chunks != need) return fail(MCB_ERR_INVALID, "n_chunks must be %llu", (unsigned long long)need);
+    DeviceGuard g(e->device);
+    if ((rc = e->partials.reserve((size_t)need + 1))) return rc;
+    const EuropeanParams prm = european_params(opt, opt->K, opt->v, n_paths, seed, 0);
+    if ((rc = launch_european<MCB_EUROPEAN_PATHS_PER_SLOT>(e, prm, option_type, need, e->partials.ptr, nullptr, 0,
+                                                           e->stream)))
+        return rc;
+    CU(cudaMemcpyAsync(partials, e->partials.ptr, (size_t)need * sizeof(float2), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return MCB_OK;
+}
+
+int mcb_bullet_payoffs(mcb_engine *e, const mcb_option_data *opt, uint64_t first_path, uint64_t n_paths, uint64_t seed,
+                       int Ik, float Sk, int Tk, float *payoffs)
+{
+    int rc = check_common(e, opt);
+    if (rc) return rc;
+    if (!payoffs) return fail(MCB_ERR_INVALID, "payoffs is NULL");
+    if (n_paths == 0) return MCB_OK;
+    DeviceGuard g(e->device);
+    const uint64_t c_lo = first_path / kBulletChunk;
+    const uint64_t c_hi = (first_path + n_paths + kBulletChunk - 1) / kBulletChunk;
+    if (c_hi - c_lo > 0x7fffffffull) return fail(MCB_ERR_INVALID, "too many chunks for one launch");
+    if ((rc = e->partials.reserve((size_t)(c_hi - c_lo) + 1))) return rc;
+    if ((rc = e->scratch.reserve((size_t)n_paths * sizeof(float)))) return rc;
+    float *d = reinterpret_cast<float *>(e->scratch.ptr);
+    WalkParams prm;
+    if ((rc = bullet_params(opt, first_path + n_paths, seed, Ik, Sk, Tk, c_lo, &prm))) return rc;
+    bullet_kernel<MCB_BULLET_PATHS_PER_SLOT><<<(unsigned)(c_hi - c_lo), kSlots, 0, e->stream>>>(prm, e->partials.ptr, d,
+                                                                                                first_path);
+    e->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(payoffs, d, (size_t)n_paths * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return MCB_OK;
+}
+
+int mcb_last_segments(mcb_engine *e, double *segments)
+{
+    if (!e || !segments) return fail(MCB_ERR_INVALID, "NULL argument");
+    memcpy(segments, e->h_segments, sizeof(double) * 2 * MCB_SEGMENTS);
+    return MCB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,147 @@
+// philox.cuh -- stateless Philox4x32-10 stream + Box-Muller normals, sm_100a device code.
+//
+// Replaces the reference's stateful XORWOW generator: setup_kernel / curand_init(seed, tid, 0)
+// (inc/tool.cuh:192-195) and curand_normal(&state) at every call site
+// (inc/trajectories.cuh:74,145,223,301; inc/nmc.cuh:56,152,223,336; inc/testing.cuh:67).
+// The integer words are bit-identical to cuRAND's curandStatePhilox4_32_10_t stream
+// curand_init(seed, subsequence, offset = 0): block b of subsequence p is
+// Philox(ctr = (b_lo, b_hi, p_lo, p_hi), key = (seed_lo, seed_hi)).  No state is stored:
+// the counter is a function of (path id, step), so there is no setup kernel and no 48-byte
+// per-thread state traffic.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace mcb {
+
+constexpr uint32_t kPhiloxM0 = 0xD2511F53u;
+constexpr uint32_t kPhiloxM1 = 0xCD9E8D57u;
+constexpr uint32_t kPhiloxW0 = 0x9E3779B9u;
+constexpr uint32_t kPhiloxW1 = 0xBB67AE85u;
+
+// The ten round keys are thread-invariant: they are expanded once on the host and live in
+// the kernel's constant bank, so the key schedule costs no instructions on the device.
+struct PhiloxKeys {
+    uint32_t k0[10];
+    uint32_t k1[10];
+};
+
+inline PhiloxKeys make_philox_keys(uint64_t seed)
+{
+    PhiloxKeys k;
+    uint32_t a = (uint32_t)seed, b = (uint32_t)(seed >> 32);
+    for (int i = 0; i < 10; ++i) {
+        k.k0[i] = a;
+        k.k1[i] = b;
+        a += kPhiloxW0;
+        b += kPhiloxW1;
+    }
+    return k;
+}
+
+struct Words4 {
+    uint32_t x, y, z, w;
+};
+
+// One round: 2 IMAD.WIDE.U32 + 2 LOP3 (three-input xor).
+__device__ __forceinline__ void philox_round(uint32_t &c0, uint32_t &c1, uint32_t &c2, uint32_t &c3,
+                                             uint32_t k0, uint32_t k1)
+{
+    const uint64_t p0 = (uint64_t)kPhiloxM0 * c0;
+    const uint64_t p1 = (uint64_t)kPhiloxM1 * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+    c1 = (uint32_t)p1;
+    c3 = (uint32_t)p0;
+    c0 = n0;
+    c2 = n2;
+}
+
+// Full bijection.  When the caller passes literal zeros for the block counter (single-step
+// pricing: block 0) the first round's M0 product folds away at compile time, the second
+// round's M1 product is loop-invariant (it depends only on p_hi and the key), and unused
+// output words are dead-code-eliminated round by round.
+__device__ __forceinline__ Words4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                const PhiloxKeys &k)
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) philox_round(c0, c1, c2, c3, k.k0[r], k.k1[r]);
+    return Words4{c0, c1, c2, c3};
+}
+
+// ---- Box-Muller on the MUFU (XU) pipe -------------------------------------------------
+// cuRAND's _curand_box_muller (curand_normal.h:70-88): u = x*2^-32 + 2^-33 in (0,1],
+// v = y*2pi*2^-32 + half a step; normal pair (s sin v, s cos v), s = sqrt(-2 ln u).
+// Here ln comes from MUFU.LG2, the root from MUFU.SQRT and sin/cos from MUFU.SIN/COS.
+// The angle word is converted as a SIGNED integer: (int)y*2pi*2^-32 differs from cuRAND's
+// unsigned form by exactly 2pi when y >= 2^31, i.e. it is the same angle, but it lands in
+// [-pi, pi) where MUFU.SIN/COS are most accurate (|err| <= 2^-21.4).
+
+__device__ __forceinline__ float mufu_lg2(float x)
+{
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float mufu_ex2(float x)
+{
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float mufu_sqrt(float x)
+{
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float mufu_sin(float x)
+{
+    float r;
+    asm("sin.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float mufu_cos(float x)
+{
+    float r;
+    asm("cos.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+constexpr float k2Pow32Inv = 2.3283064e-10f;                 // CURAND_2POW32_INV
+constexpr float k2Pow32Inv2Pi = 2.3283064e-10f * 6.2831855f; // CURAND_2POW32_INV_2PI
+constexpr float kMinus2Ln2 = -1.3862943611198906f;           // -2 ln 2
+
+// s = sqrt(-2 ln u) : I2FP, FFMA, MUFU.LG2, FMUL, MUFU.SQRT
+__device__ __forceinline__ float bm_radius(uint32_t x)
+{
+    const float u = fmaf(__uint2float_rn(x), k2Pow32Inv, 0.5f * k2Pow32Inv);
+    return mufu_sqrt(kMinus2Ln2 * mufu_lg2(u));
+}
+
+// v in [-pi, pi) : I2FP, FFMA
+__device__ __forceinline__ float bm_angle(uint32_t y)
+{
+    return fmaf(__int2float_rn((int)y), k2Pow32Inv2Pi, 0.5f * k2Pow32Inv2Pi);
+}
+
+// normal 0 of a Philox block (the even, "sin" member of the first pair)
+__device__ __forceinline__ float normal_sin(uint32_t x, uint32_t y)
+{
+    return bm_radius(x) * mufu_sin(bm_angle(y));
+}
+
+// all four normals of a Philox block, in curand_normal order, each shifted by `shift`:
+// z[j] = normal_j + shift.  Multi-step walks pass shift = drift/vol so that one FFMA per step
+// (l += vol * z) applies drift and diffusion together; shift = 0 gives the plain normals.
+__device__ __forceinline__ void normals4(const Words4 &w, float shift, float z[4])
+{
+    const float s0 = bm_radius(w.x), v0 = bm_angle(w.y);
+    const float s1 = bm_radius(w.z), v1 = bm_angle(w.w);
+    z[0] = fmaf(s0, mufu_sin(v0), shift);
+    z[1] = fmaf(s0, mufu_cos(v0), shift);
+    z[2] = fmaf(s1, mufu_sin(v1), shift);
+    z[3] = fmaf(s1, mufu_cos(v1), shift);
+}
+
+}  // namespace mcb

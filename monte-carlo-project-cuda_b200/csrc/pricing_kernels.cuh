@@ -1,0 +1,278 @@
+// pricing_kernels.cuh -- the GBM hot path: European, bullet, reductions.  sm_100a only.
+//
+// Replaces (reference file:line, relative to the reference repo)
+//   simulateOptionPriceMultipleBlockGPUwithReduce      inc/trajectories.cuh:54-113
+//   simulateBulletOptionPriceMultipleBlockGPU[atomic]  inc/trajectories.cuh:115-271
+//   reduce3..6 + host/atomic final sums                inc/reduce.cuh, inc/wrappers.cuh:81-84
+// Design: no RNG state, many paths per thread, payoff (sum, sumsq) accumulated in
+// registers, one chunk partial per CTA, fixed-order double-precision final passes.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "block_reduce.cuh"
+#include "philox.cuh"
+
+namespace mcb {
+
+enum { kCall = 0, kPut = 1 };
+
+// ------------------------------------------------------------------------------------------
+// European option, one GBM step, canonical (seed, path id) keying.
+//   St = S0 exp((r - sigma^2/2) T + sigma sqrt(T) G)  ->  St = 2^(c0 + c1 z)
+// with c0 = log2 S0 + (r - sigma^2/2) T log2 e and c1 = sigma sqrt(T) log2 e folded on the
+// host, so a path is: Philox (block 0) -> Box-Muller sin branch -> FFMA -> MUFU.EX2 -> payoff.
+// ------------------------------------------------------------------------------------------
+struct EuropeanParams {
+    float c0, c1, K;
+    uint32_t pad;
+    uint64_t n_paths;      // total paths of the run (ragged tail lives in the last chunk)
+    uint64_t first_chunk;  // chunk index of blockIdx.x == 0
+    PhiloxKeys keys;
+};
+
+template <int TYPE>
+__device__ __forceinline__ float european_payoff(uint32_t p_lo, uint32_t p_hi, const EuropeanParams &prm)
+{
+    const Words4 w = philox4x32_10(0u, 0u, p_lo, p_hi, prm.keys);
+    const float z = normal_sin(w.x, w.y);
+    const float St = mufu_ex2(fmaf(prm.c1, z, prm.c0));
+    return TYPE == kPut ? fmaxf(prm.K - St, 0.0f) : fmaxf(St - prm.K, 0.0f);
+}
+
+// One CTA = one chunk of kSlots * PPS consecutive paths.  Slot t (= thread t) accumulates
+// chunk-local paths t, t+256, ... in that order; partials[chunk - first_chunk] = (sum, sumsq).
+// payoffs (nullable) receives every path's payoff (parity hook).
+template <int TYPE, int PPS>
+__global__ void __launch_bounds__(kSlots)
+european_kernel(const __grid_constant__ EuropeanParams prm, float2 *__restrict__ partials,
+                float *__restrict__ payoffs, uint64_t payoffs_first_path)
+{
+    __shared__ float scratch[2 * kWarps];
+    const uint64_t chunk = prm.first_chunk + blockIdx.x;
+    const uint64_t base = chunk * (uint64_t)(kSlots * PPS);
+    // a chunk never straddles a multiple of 2^32, so the high counter word is CTA-uniform
+    const uint32_t p_hi = (uint32_t)(base >> 32);
+    const uint32_t p_lo0 = (uint32_t)base + threadIdx.x;
+    const uint64_t left = prm.n_paths - base;  // > 0 by construction of the grid
+
+    float sum = 0.0f, sq = 0.0f;
+    if (left >= (uint64_t)(kSlots * PPS) && payoffs == nullptr) {
+#pragma unroll 4
+        for (int i = 0; i < PPS; ++i) {
+            const float pay = european_payoff<TYPE>(p_lo0 + (uint32_t)(i * kSlots), p_hi, prm);
+            sum = sum + pay;
+            sq = fmaf(pay, pay, sq);
+        }
+    } else {
+        for (int i = 0; i < PPS; ++i) {
+            const uint32_t local = (uint32_t)(i * kSlots) + threadIdx.x;
+            if ((uint64_t)local < left) {
+                const float pay = european_payoff<TYPE>(p_lo0 + (uint32_t)(i * kSlots), p_hi, prm);
+                sum = sum + pay;
+                sq = fmaf(pay, pay, sq);
+                if (payoffs && base + local >= payoffs_first_path) payoffs[base + local - payoffs_first_path] = pay;
+            }
+        }
+    }
+    block_fold2(sum, sq, scratch);
+    if (threadIdx.x == 0) partials[blockIdx.x] = make_float2(sum, sq);
+}
+
+// ------------------------------------------------------------------------------------------
+// Multi-step GBM walk in log2 space, fused drift + diffusion: with dz = drift/vol folded
+// into the normal (z' = z + dz, the FFMA that scales the Box-Muller radius anyway) a step is
+// ONE FFMA, l += v z'; the barrier test is l < log2 B; one MUFU.EX2 at the end.  One Philox
+// block feeds four steps.
+// ------------------------------------------------------------------------------------------
+struct WalkParams {
+    float l0;      // log2 of the start price
+    float dz;      // drift / vol = (r - sigma^2/2) sqrt(dt) / sigma
+    float v;       // sigma sqrt(dt) log2 e   (> 0)
+    float lB;      // log2 B  (-inf when B <= 0: the barrier is never hit)
+    float K;
+    int P1, P2;
+    int n_steps;   // steps to walk
+    int count0;    // initial barrier count (Ik)
+    uint32_t pad;
+    uint64_t n_paths;
+    uint64_t first_chunk;
+    PhiloxKeys keys;
+};
+
+// Walk `n_steps` steps of stream (keys, subsequence) from (l, count); normal i of the stream
+// drives step i.
+__device__ __forceinline__ void walk_path(float &l, int &count, uint32_t s_lo, uint32_t s_hi, int n_steps,
+                                          float dz, float v, float lB, const PhiloxKeys &keys)
+{
+    const int full = n_steps >> 2;
+    for (int b = 0; b < full; ++b) {
+        float z[4];
+        normals4(philox4x32_10((uint32_t)b, 0u, s_lo, s_hi, keys), dz, z);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            l = fmaf(v, z[j], l);
+            count += (l < lB) ? 1 : 0;
+        }
+    }
+    const int tail = n_steps & 3;
+    if (tail) {
+        float z[4];
+        normals4(philox4x32_10((uint32_t)full, 0u, s_lo, s_hi, keys), dz, z);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            if (j < tail) {
+                l = fmaf(v, z[j], l);
+                count += (l < lB) ? 1 : 0;
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ float bullet_payoff_from(float l, int count, const WalkParams &prm)
+{
+    const float pay = fmaxf(mufu_ex2(l) - prm.K, 0.0f);
+    return (count >= prm.P1 && count <= prm.P2) ? pay : 0.0f;
+}
+
+template <int PPS>
+__global__ void __launch_bounds__(kSlots)
+bullet_kernel(const __grid_constant__ WalkParams prm, float2 *__restrict__ partials,
+              float *__restrict__ payoffs, uint64_t payoffs_first_path)
+{
+    __shared__ float scratch[2 * kWarps];
+    const uint64_t chunk = prm.first_chunk + blockIdx.x;
+    const uint64_t base = chunk * (uint64_t)(kSlots * PPS);
+    const uint64_t left = prm.n_paths - base;
+    float sum = 0.0f, sq = 0.0f;
+#pragma unroll 1
+    for (int i = 0; i < PPS; ++i) {
+        const uint32_t local = (uint32_t)(i * kSlots) + threadIdx.x;
+        if ((uint64_t)local < left) {
+            const uint64_t p = base + local;
+            float l = prm.l0;
+            int count = prm.count0;
+            walk_path(l, count, (uint32_t)p, (uint32_t)(p >> 32), prm.n_steps, prm.dz, prm.v, prm.lB, prm.keys);
+            const float pay = bullet_payoff_from(l, count, prm);
+            sum = sum + pay;
+            sq = fmaf(pay, pay, sq);
+            if (payoffs && p >= payoffs_first_path) payoffs[p - payoffs_first_path] = pay;
+        }
+    }
+    block_fold2(sum, sq, scratch);
+    if (threadIdx.x == 0) partials[blockIdx.x] = make_float2(sum, sq);
+}
+
+// ------------------------------------------------------------------------------------------
+// Final passes (replace the float atomicAdd / host loop of the reference).
+// segment_kernel: CTA s folds the chunk partials of segment s in double, fixed order.
+//   partials is indexed by (chunk - partials_first_chunk); segments outside [seg_lo, seg_hi)
+//   are written as +0.0 so a sum-allreduce over ranks reproduces every segment exactly.
+// combine_kernel: one warp folds the 64 segments and finalises price + standard error.
+// Both are batched over parameter sets with blockIdx.y / blockIdx.x.
+// ------------------------------------------------------------------------------------------
+constexpr int kSegments = 64;  // MCB_SEGMENTS
+
+__global__ void __launch_bounds__(kSlots)
+segment_kernel(const float2 *__restrict__ partials, uint64_t partials_stride, uint64_t partials_first_chunk,
+               uint64_t n_chunks, int seg_lo, int seg_hi, double *__restrict__ segments)
+{
+    __shared__ double scratch[2 * kWarps];
+    const int seg = blockIdx.x;
+    const int set = blockIdx.y;
+    double a = 0.0, b = 0.0;
+    if (seg >= seg_lo && seg < seg_hi) {
+        const uint64_t lo = (n_chunks * (uint64_t)seg) / kSegments;
+        const uint64_t hi = (n_chunks * (uint64_t)(seg + 1)) / kSegments;
+        const float2 *src = partials + (uint64_t)set * partials_stride;
+        for (uint64_t c = lo + threadIdx.x; c < hi; c += kSlots) {
+            const float2 v = src[c - partials_first_chunk];
+            a = a + (double)v.x;
+            b = b + (double)v.y;
+        }
+    }
+    block_fold2(a, b, scratch);
+    if (threadIdx.x == 0) {
+        double *dst = segments + ((uint64_t)set * kSegments + seg) * 2;
+        dst[0] = a;
+        dst[1] = b;
+    }
+}
+
+struct ResultDev {  // == mcb_result
+    double price, std_error, sum, sumsq;
+    uint64_t n_paths;
+};
+
+__global__ void __launch_bounds__(32)
+combine_kernel(const double *__restrict__ segments, uint64_t n_paths, double discount, ResultDev *__restrict__ out)
+{
+    const int set = blockIdx.x, lane = threadIdx.x;
+    const double *seg = segments + (uint64_t)set * kSegments * 2;
+    double s = seg[2 * lane] + seg[2 * (lane + 32)];
+    double q = seg[2 * lane + 1] + seg[2 * (lane + 32) + 1];
+    s = warp_fold(s);
+    q = warp_fold(q);
+    if (lane == 0) {
+        const double n = (double)n_paths;
+        const double mean = s / n;
+        double var = q / n - mean * mean;
+        var = var > 0.0 ? var : 0.0;
+        if (n_paths > 1) var *= n / (n - 1.0);
+        ResultDev r;
+        r.price = discount * mean;
+        r.std_error = discount * sqrt(var / n);
+        r.sum = s;
+        r.sumsq = q;
+        r.n_paths = n_paths;
+        out[set] = r;
+    }
+}
+
+// Standalone deterministic float sum (reduce3..6 replacement): slot t adds x[t], x[t+256], ...
+__global__ void __launch_bounds__(kSlots)
+reduce_sum_kernel(const float *__restrict__ x, uint64_t n, float *__restrict__ out)
+{
+    __shared__ float scratch[2 * kWarps];
+    float a = 0.0f, b = 0.0f;
+    for (uint64_t i = threadIdx.x; i < n; i += kSlots) a = a + x[i];
+    block_fold2(a, b, scratch);
+    if (threadIdx.x == 0) out[0] = a;
+}
+
+// Pricing from pre-generated normals (inc/trajectories.cuh:14-52): thread per path.
+__global__ void __launch_bounds__(kSlots)
+pregen_kernel(const float *__restrict__ normals, uint64_t n_paths, int n_steps, float l0, float dz, float v,
+              float K, float *__restrict__ payoffs)
+{
+    const uint64_t p = (uint64_t)blockIdx.x * kSlots + threadIdx.x;
+    if (p >= n_paths) return;
+    float l = l0;
+    const float *z = normals + p * (uint64_t)n_steps;
+    for (int i = 0; i < n_steps; ++i) l = fmaf(v, z[i] + dz, l);
+    payoffs[p] = fmaxf(mufu_ex2(l) - K, 0.0f);
+}
+
+// ---- parity hooks ---------------------------------------------------------------------
+__global__ void philox_blocks_kernel(PhiloxKeys keys, const uint64_t *__restrict__ subseq,
+                                     const uint64_t *__restrict__ block, uint64_t n, uint4 *__restrict__ out)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t s = subseq[i], b = block[i];
+    const Words4 w = philox4x32_10((uint32_t)b, (uint32_t)(b >> 32), (uint32_t)s, (uint32_t)(s >> 32), keys);
+    out[i] = make_uint4(w.x, w.y, w.z, w.w);
+}
+
+__global__ void stream_normals_kernel(PhiloxKeys keys, uint64_t subseq, uint64_t n0, uint64_t count,
+                                      float *__restrict__ out)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const uint64_t n = n0 + i, b = n >> 2;
+    float z[4];
+    normals4(philox4x32_10((uint32_t)b, (uint32_t)(b >> 32), (uint32_t)subseq, (uint32_t)(subseq >> 32), keys), 0.0f, z);
+    out[i] = z[n & 3];
+}
+
+}  // namespace mcb

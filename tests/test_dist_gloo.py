@@ -1,0 +1,70 @@
+"""world_size-2 (and 3) gloo runs of the multi-GPU combine: each rank fills only the segments
+it owns, one sum-allreduce makes every rank hold all 64, the fixed final tree gives bits that
+do not depend on the world size.  The oracle stands in for the GPU kernel (CPU box)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, n_paths, out_dir):
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as entry
+    import oracle
+    pkg = entry.load_package()
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        chunk = pkg.EUROPEAN_CHUNK
+        n_chunks = (n_paths + chunk - 1) // chunk
+        seg_lo, seg_hi, c_lo, c_hi = pkg.segment_span(rank, world, n_chunks)
+        o = oracle.option(N_PATHS=n_paths)
+        partials = np.zeros((n_chunks, 2), dtype=np.float32)
+        for c in range(c_lo, c_hi):
+            first = c * chunk
+            cnt = min(chunk, n_paths - first)
+            _, _, pay = oracle.european(o, first, cnt, 1234, oracle.CALL, want_payoffs=True)
+            buf = np.zeros(chunk, dtype=np.float32)
+            buf[:cnt] = pay
+            partials[c] = oracle.chunk_tree_f32(buf, cnt, pkg.EUROPEAN_PATHS_PER_SLOT)
+        seg = oracle.segment_tree_f64(partials)
+        mine = np.zeros_like(seg)
+        mine[seg_lo:seg_hi] = seg[seg_lo:seg_hi]       # +0.0 outside the owned range
+        t = torch.from_numpy(mine)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        s, q = oracle.final_tree_f64(t.numpy())
+        np.save(os.path.join(out_dir, f"r{rank}.npy"), np.array([s, q]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_combine_is_bit_identical(tmp_path, world, orc, pkg):
+    n_paths = 5 * pkg.EUROPEAN_CHUNK + 1234   # ragged tail, 6 chunks
+    port = 29500 + (os.getpid() % 2000) + world
+    mp.spawn(_worker, args=(world, port, n_paths, str(tmp_path)), nprocs=world, join=True)
+    got = [np.load(tmp_path / f"r{r}.npy") for r in range(world)]
+    # single-rank truth
+    o = orc.option(N_PATHS=n_paths)
+    chunk = pkg.EUROPEAN_CHUNK
+    partials = []
+    for c in range(6):
+        first = c * chunk
+        cnt = min(chunk, n_paths - first)
+        _, _, pay = orc.european(o, first, cnt, 1234, orc.CALL, want_payoffs=True)
+        buf = np.zeros(chunk, dtype=np.float32)
+        buf[:cnt] = pay
+        partials.append(orc.chunk_tree_f32(buf, cnt, pkg.EUROPEAN_PATHS_PER_SLOT))
+    seg = orc.segment_tree_f64(np.array(partials, dtype=np.float32))
+    s, q = orc.final_tree_f64(seg)
+    for g in got:
+        assert g[0] == s and g[1] == q      # bit-identical on every rank, for every world size
+    ds, _ = orc.european(o, 0, n_paths, 1234, orc.CALL)
+    assert s == pytest.approx(ds, rel=1e-6)
