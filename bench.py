@@ -1,0 +1,448 @@
+#!/usr/bin/env python
+"""bench.py -- the headline measurement: GBM paths/sec, European call, 2^30 paths per B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+A "step" is one pass of the hot path: pricing a European call (BASELINE.json configs[1]:
+S0=100 K=100 r=0.05 sigma=0.2 T=1, single step) on 2^30 paths PER GPU (weak scaling: N GPUs
+price one N*2^30-path job sharded by path index, one NCCL allreduce of the 1 KiB segment vector,
+bit-identical price for any N).  Rank 0 prints ONE JSON line.
+
+  value    : whole-job paths/s, device-timed (CUDA events, max over ranks), nothing to stage in HBM
+             (the path has no input arrays: a path is a pure function of (seed, path id)).
+  e2e      : the same metric through the public synchronous C-ABI call mcb_price_european
+             (host OptionData in, host mcb_result out, stream sync + D2H inside the timed region).
+  roofline : dominant kernel european_kernel against the SM issue roofline (north_star: "FP32/SFU
+             compute roofline" -- nothing here touches HBM or tensor cores), algorithmic
+             thread-instructions per path from SURVEY.md 8(d); plus `roofline_trajectory`, the
+             HBM-bound trajectory-store kernel (configs[2]) against MEASURED_PEAKS.json hbm_gbs.
+  cpu_baseline : the UNMODIFIED reference CPU pricer (oracle/_ref, simulateOptionPriceCPU,
+             inc/tool.cuh:104-130) on this box's host cores, bounded sample.  Reported, not a target.
+
+`--impl reference` times only that CPU pricer (rank 0; other ranks exit 0).
+oracle/ is used here ONLY as cpu_baseline / reference arm, never on the measured GPU path.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "GBM paths/sec (European call, 2^30 paths per GPU)"
+UNIT = "paths/s"
+PATHS_PER_GPU = 1 << 30
+CFG = dict(S0=100.0, K=100.0, r=0.05, v=0.2, T=1.0)
+SEED = 1234
+
+# Algorithmic work per unit (restated in DESIGN.md "Rooflines")
+INSTR_PER_EUROPEAN_PATH = 57          # 42 INT + 11 FP32 + 4 MUFU thread-instructions, canonical keying
+ISSUE_PER_CLK_PER_SM = 128            # 4 schedulers x 32 lanes
+BYTES_PER_TRAJECTORY_STEP = 4         # one float stored per path-step
+TRAJ_PATHS, TRAJ_STEPS = 1 << 20, 252
+
+
+def bs_call(S0, K, T, r, v):
+    d1 = (math.log(S0 / K) + (r + 0.5 * v * v) * T) / (v * math.sqrt(T))
+    d2 = d1 - v * math.sqrt(T)
+    phi = lambda x: 0.5 * math.erfc(-x / math.sqrt(2.0))
+    return S0 * phi(d1) - K * math.exp(-r * T) * phi(d2)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return float(d.get("hbm_gbs", 6650.0)), float(d.get("sm_max_mhz", 1965.0)), "measured"
+    return 6650.0, 1965.0, "fallback"
+
+
+# ------------------------------------------------------------------------------ clock sampler
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons through NVML (what nvidia-smi prints) every 20 ms."""
+
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown",
+               0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, device_index: int):
+        super().__init__(daemon=True)
+        self.samples = []   # (t, sm_mhz, reasons_mask, phase)
+        self.phase = "idle"
+        self._halt = threading.Event()
+        self.max_mhz = None
+        self.ok = False
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            try:
+                uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception as exc:  # NVML missing: the JSON says so instead of inventing clocks
+            self.err = repr(exc)
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        while not self._halt.is_set():
+            try:
+                mhz = int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.samples.append((time.perf_counter(), mhz, mask, self.phase))
+            except Exception:
+                pass
+            self._halt.wait(0.02)
+
+    def stop(self):
+        self._halt.set()
+
+    def summary(self):
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "error": getattr(self, "err", "nvml")}
+        timed = [s for s in self.samples if s[3] == "timed"]
+        used = timed if len(timed) >= 3 else [s for s in self.samples if s[3] != "idle"]
+        mhz = sorted(s[1] for s in used)
+        mask = 0
+        for s in used:
+            mask |= s[2]
+        return {"sm_mhz": mhz[len(mhz) // 2] if mhz else None, "sm_max_mhz": self.max_mhz,
+                "reasons": [name for bit, name in self.REASONS.items() if mask & bit],
+                "samples": len(used), "window": "timed" if used is timed else "all load phases"}
+
+
+# ----------------------------------------------------------------------------- reference arm
+def reference_rate(threads: int, paths_per_thread: int, chunk: int = 1 << 20):
+    """The unmodified reference CPU pricer on `threads` host threads (ctypes releases the GIL).
+    Calls of 2^20 paths each: its single float accumulator is only valid to ~1e6-1e7 paths per
+    call.  Returns (paths/s, seconds, mean price, kind)."""
+    import ctypes as C
+    import oracle
+
+    o = oracle.option(N_PATHS=chunk, **CFG)
+    if oracle.have_ref():
+        ref = oracle.ref_cpu()
+        kind = "reference"
+
+        def work(out, i):
+            done = C.c_uint64()
+            out[i] = ref.ref_vanilla_cpu_chunked(C.byref(o), paths_per_thread, chunk, C.byref(done))
+    else:  # oracle/_ref did not travel: fall back to the plain-C port (still CPU, still not the product)
+        kind = "port"
+
+        def work(out, i):
+            s, _ = oracle.european(o, i * paths_per_thread, paths_per_thread, SEED, oracle.CALL)
+            out[i] = oracle.price_from_sum(s, paths_per_thread, o.r, o.T)
+
+    out = [0.0] * threads
+    ts = [threading.Thread(target=work, args=(out, i)) for i in range(threads)]
+    t0 = time.perf_counter()
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    dt = time.perf_counter() - t0
+    return threads * paths_per_thread / dt, dt, sum(out) / threads, kind
+
+
+def host_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import oracle
+    oracle.lib()
+    threads = host_threads()
+    # calibrate on one thread, then size a step so the whole run stays within ~2 minutes
+    rate1, _, _, kind = reference_rate(1, 1 << 21)
+    budget = min(1.5, 110.0 / max(1, args.steps + args.warmup))
+    per_thread = max(1 << 20, int(rate1 * budget) >> 20 << 20)
+    for _ in range(args.warmup):
+        reference_rate(threads, per_thread)
+    t_total, price = 0.0, 0.0
+    for _ in range(args.steps):
+        _, dt, p, kind = reference_rate(threads, per_thread)
+        t_total += dt
+        price += p
+    paths = threads * per_thread
+    value = paths * args.steps / t_total
+    sample = f"{threads} threads x {per_thread} paths per step in calls of 2^20 (of the 2^30-path workload)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "European call S0=100 K=100 r=0.05 sigma=0.2 T=1, single step, CPU "
+                               "simulateOptionPriceCPU (inc/tool.cuh:104-130), bounded sample", **CFG},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample,
+                         "value_1core": rate1},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "price": price / args.steps, "closed_form": bs_call(**CFG),
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ----------------------------------------------------------------------------------- own arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as entry
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if args.gpus > 1 and world == 1:
+        raise SystemExit("launch N>1 with torch.distributed.run (one process per GPU)")
+    if not torch.cuda.is_available():
+        raise SystemExit("no CUDA device: this engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    pkg = entry.load_package()
+    import importlib
+    sharded = importlib.import_module(entry.PKG_NAME + ".sharded")
+    eng = pkg.Engine(local)
+    pricer = sharded.ShardedPricer(eng)
+    hbm_gbs, sm_max_mhz, peak_src = measured_peaks()
+
+    n_total = PATHS_PER_GPU * world
+    opt = pkg.option(N_PATHS=PATHS_PER_GPU, **CFG)
+    sampler = ClockSampler(local)
+    sampler.start()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-timed leg -------------------------------------------------------------
+    # everything is enqueued on ONE real stream (the C-ABI reads NULL as "engine stream", and
+    # torch.cuda.Event only sees torch's current stream): kernels, the NCCL allreduce, the events.
+    torch.cuda.set_stream(pricer.stream)
+    sampler.phase = "warmup"
+    for _ in range(max(args.warmup, 3)):
+        pricer.european_async(opt, n_total, SEED, pkg.CALL)
+    barrier()
+    eng.timing_read(pkg.KERNEL_EUROPEAN)
+    eng.timing_enable(True)
+    launches0 = eng.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.phase = "timed"
+    ev0.record()
+    for _ in range(args.steps):
+        pricer.european_async(opt, n_total, SEED, pkg.CALL)
+    ev1.record()
+    barrier()
+    sampler.phase = "post"
+    ms_total = max_over_ranks(float(ev0.elapsed_time(ev1)))
+    launches = eng.launch_count - launches0
+    eng.timing_enable(False)
+    kern_ms, kern_n = eng.timing_read(pkg.KERNEL_EUROPEAN)
+    result = pricer._fetch(1)[0]
+    assert 0.2 < kern_ms / max(ms_total, 1e-9) <= 1.0 + 1e-3 and kern_n == args.steps, \
+        f"kernel events ({kern_ms:.3f} ms / {kern_n}) do not fit inside the timed region ({ms_total:.3f} ms)"
+    value = n_total * args.steps / (ms_total * 1e-3)
+
+    # ---- end-to-end leg: the public synchronous call, host in / host out ----------------
+    sampler.phase = "e2e"
+    call = (lambda: pricer.price_european(opt, n_total, SEED, pkg.CALL)) if world > 1 else \
+        (lambda: eng.price_european(opt, n_total, SEED, pkg.CALL))
+    for _ in range(3):
+        call()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_res = call()
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = n_total * args.steps / e2e_s
+    # bytes: OptionData + Philox round keys travel as kernel parameters; the result (40 B) and the
+    # 64 double segments (1 KiB, kept for mcb_last_segments) come back
+    h2d = 48 + 80
+    d2h = 40 + (0 if world > 1 else 1024)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"European call S0=100 K=100 r=0.05 sigma=0.2 T=1, single step, 2^30 paths per GPU "
+                               f"({n_total} paths total), seed {SEED}, Philox4x32-10 keyed by (seed, path id)",
+                   "paths_per_gpu": PATHS_PER_GPU, "parallelism": f"path-index shards x{world}, one allreduce of 1 KiB",
+                   "l2": "n/a: the kernel reads no global memory (64 Ki chunk partials of 8 B written per launch)",
+                   **CFG},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "api": "mcb_price_european" if world == 1 else "ShardedPricer.price_european",
+                "ms_per_step": 1e3 * e2e_s / args.steps},
+        "gpu_launches": int(launches),
+        "price": result.price, "std_error": result.std_error, "closed_form": bs_call(**CFG),
+        "z_score": (result.price - bs_call(**CFG)) / result.std_error,
+        "e2e_price_bits_equal": bool(e2e_res.sum == result.sum and e2e_res.sumsq == result.sumsq),
+    }
+    if kern_n:
+        per_launch_s = kern_ms * 1e-3 / kern_n
+        paths_per_launch = PATHS_PER_GPU  # this rank's shard: n_total / world
+        achieved = INSTR_PER_EUROPEAN_PATH * paths_per_launch / per_launch_s / 1e12
+        sms = eng.device_info().sm_count
+        peak = sms * ISSUE_PER_CLK_PER_SM * sm_max_mhz * 1e6 / 1e12
+        line["roofline"] = {
+            "bound": "issue", "kernel": "european_kernel", "achieved": achieved, "peak": peak, "unit": "Tinstr/s",
+            "frac": achieved / peak, "traffic": None,
+            "per_unit": f"{INSTR_PER_EUROPEAN_PATH} thread-instr/path (SURVEY 8(d))",
+            "peak_how": f"{sms} SMs x {ISSUE_PER_CLK_PER_SM} thread-instr/clk x {sm_max_mhz:.0f} MHz ({peak_src} sm_max_mhz)",
+            "kernel_ms": 1e3 * per_launch_s, "kernel_launches": kern_n,
+            "kernel_paths_per_s": paths_per_launch / per_launch_s,
+            "kernel_share_of_step": kern_ms / kern_n / (ms_total / args.steps),
+        }
+
+    # ---- other configs of BASELINE.json (rank 0, N = 1 only): bounded, each device-timed ----
+    if world == 1 and not args.headline_only:
+        sampler.phase = "extra"
+        try:
+            line["roofline_trajectory"], line["other_workloads"] = other_workloads(torch, pkg, eng, hbm_gbs, peak_src)
+        except Exception as exc:  # never lose the headline line to a secondary leg
+            line["other_workloads_error"] = repr(exc)
+
+    sampler.stop()
+    sampler.join(timeout=1.0)
+    clocks = sampler.summary()
+    line["clocks"] = clocks
+    if clocks.get("sm_mhz") and "roofline" in line:
+        rf = line["roofline"]
+        rf["frac_at_sampled_clock"] = rf["achieved"] / (rf["peak"] * clocks["sm_mhz"] / sm_max_mhz)
+
+    # ---- CPU baseline (rank 0, N = 1 only) ---------------------------------------------
+    if world == 1 and rank == 0 and not args.no_cpu_baseline:
+        threads = host_threads()
+        rate1, _, _, kind = reference_rate(1, 1 << 22)
+        per_thread = max(1 << 20, int(rate1 * 12.0) >> 20 << 20)   # ~12 s of CPU work per thread
+        rate, dt, price, kind = reference_rate(threads, per_thread)
+        line["cpu_baseline"] = {
+            "value": rate, "unit": UNIT, "cores": threads, "kind": kind,
+            "sample": f"{threads} threads x {per_thread} paths ({dt:.1f} s) of the 2^30-path workload, "
+                      f"calls of 2^20 paths", "value_1core": rate1, "price": price,
+        }
+
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def other_workloads(torch, pkg, eng, hbm_gbs, peak_src):
+    """configs[2] trajectories (HBM roofline), configs[3] nested MC, configs[4] sweep, bullet."""
+    stream = torch.cuda.current_stream().cuda_stream
+    out = {}
+
+    def timed(fn, reps, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) * 1e-3 / reps
+
+    # configs[2]: 2^20 paths x 252 steps stored path-major to HBM (1.06 GB per launch > 126 MB L2)
+    opt = pkg.option(N_STEPS=TRAJ_STEPS, N_PATHS=TRAJ_PATHS, B=120.0, **CFG)
+    buf = torch.empty(TRAJ_PATHS * TRAJ_STEPS, dtype=torch.float32, device="cuda")
+    eng.timing_read(pkg.KERNEL_TRAJECTORY)
+    eng.timing_enable(True)
+    t = timed(lambda: eng.trajectories_async(opt, 0, TRAJ_PATHS, SEED, buf.data_ptr(), None, stream), 50)
+    eng.timing_enable(False)
+    kms, kn = eng.timing_read(pkg.KERNEL_TRAJECTORY)
+    nbytes = BYTES_PER_TRAJECTORY_STEP * TRAJ_PATHS * TRAJ_STEPS
+    gbs = nbytes / (kms * 1e-3 / kn) / 1e9
+    roofline_traj = {"bound": "hbm", "kernel": "trajectory_kernel", "achieved": gbs, "peak": hbm_gbs, "unit": "GB/s",
+                     "frac": gbs / hbm_gbs, "frac_of_8TBs_nominal": gbs / 8000.0, "traffic": None,
+                     "peak_how": f"MEASURED_PEAKS.json hbm_gbs ({peak_src})",
+                     "per_unit": "4 B stored per path-step", "kernel_ms": kms / kn, "kernel_launches": kn,
+                     "l2": "output 1.06 GB per launch, larger than L2"}
+    out["trajectories_2^20x252"] = {"path_steps_per_s": TRAJ_PATHS * TRAJ_STEPS / t, "GB_per_s": nbytes / t / 1e9,
+                                    "ms": 1e3 * t}
+    del buf
+
+    # bullet option, 2^22 paths x 100 steps (hello.cu parameters, r as configs[0])
+    ob = pkg.option(N_STEPS=100, N_PATHS=1 << 22, B=120.0, P1=10, P2=50, **CFG)
+    seg = torch.zeros(2 * pkg.SEGMENTS, dtype=torch.float64, device="cuda")
+    t = timed(lambda: eng.bullet_segments_async(ob, 1 << 22, SEED, 0, 0.0, 0, 0, 1, seg.data_ptr(), stream), 10)
+    out["bullet_2^22x100"] = {"path_steps_per_s": (1 << 22) * 100 / t, "ms": 1e3 * t}
+
+    # configs[3]: nested MC 4096 outer x 4096 inner x 100 steps = 8.30e10 inner path-steps
+    on = pkg.option(N_STEPS=100, N_PATHS=4096, N_PATHS_INNER=4096, B=120.0, P1=10, P2=50, **CFG)
+    F = torch.empty(4096 * 100, dtype=torch.float32, device="cuda")
+    t = timed(lambda: eng.nested_async(on, 0, 4096, 1234, 1235, pkg.DISCOUNT_COMPAT, F.data_ptr(), None, None,
+                                       stream), 2, warm=1)
+    inner_steps = 4096 * 4096 * sum(99 - k for k in range(100))
+    out["nested_4096x4096x100"] = {"inner_path_steps_per_s_upper": inner_steps / t, "ms": 1e3 * t,
+                                   "note": "upper = no early-out assumed; points with count > P2 are skipped",
+                                   "mean_F": float(F.double().mean())}
+
+    # configs[4]: 1024 parameter sets x 2^26 paths (whole job on this one GPU)
+    import numpy as np
+    K, V = np.meshgrid(np.linspace(60, 140, 32, dtype=np.float32), np.linspace(0.05, 0.8, 32, dtype=np.float32),
+                       indexing="ij")
+    os_ = pkg.option(**CFG)
+    segs = torch.zeros(1024 * 2 * pkg.SEGMENTS, dtype=torch.float64, device="cuda")
+    k, v = K.ravel().copy(), V.ravel().copy()
+    t = timed(lambda: eng.sweep_segments_async(os_, k, v, 1 << 26, SEED, pkg.CALL, 0, 1, segs.data_ptr(), stream),
+              1, warm=1)
+    out["sweep_1024x2^26"] = {"path_params_per_s": 1024 * (1 << 26) / t, "ms": 1e3 * t}
+    return roofline_traj, out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--headline-only", action="store_true", help="skip the other BASELINE configs")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.steps < 1:
+        raise SystemExit("--steps must be >= 1")
+    return run_reference(args) if args.impl == "reference" else run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -165,6 +165,16 @@ int mcb_nested_async(mcb_engine *e, const mcb_option_data *opt, uint64_t first_o
 /* Number of kernel launches this engine has issued (bench.py's gpu_launches). */
 uint64_t mcb_launch_count(mcb_engine *e);
 
+/* Per-kernel device timing for the roofline figures (no reference counterpart: the reference
+ * has no timers at all).  While enabled, every launch of a hot-path
+ * kernel is bracketed by a CUDA-event pair recorded on the launching stream;
+ * mcb_timing_read waits for the recorded launches of `kernel`, returns their summed device
+ * time and count, and forgets them. */
+enum { MCB_KERNEL_EUROPEAN = 0, MCB_KERNEL_BULLET = 1, MCB_KERNEL_TRAJECTORY = 2, MCB_KERNEL_NESTED = 3,
+       MCB_KERNEL_COUNT = 4 };
+int mcb_timing_enable(mcb_engine *e, int on);
+int mcb_timing_read(mcb_engine *e, int kernel, double *total_ms, uint64_t *launches);
+
 /* ---- parity hooks (used by tests/ to pin the integer stream and the reduction tree) -- */
 /* words[4*i..] = Philox block `blocks[i]` of subsequence `subsequences[i]` (host arrays). */
 int mcb_philox_blocks(mcb_engine *e, uint64_t seed, const uint64_t *subsequences, const uint64_t *blocks,

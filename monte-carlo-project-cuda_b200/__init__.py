@@ -36,6 +36,7 @@ DISCOUNT_COMPAT, DISCOUNT_CORRECT = 0, 1
 HOST, DEVICE = 0, 1
 
 OK, ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_NOMEM = 0, 1, 2, 3, 4
+KERNEL_EUROPEAN, KERNEL_BULLET, KERNEL_TRAJECTORY, KERNEL_NESTED = 0, 1, 2, 3
 
 
 class McbError(RuntimeError):
@@ -110,6 +111,8 @@ SIGNATURES = {
     "mcb_trajectories_async": (C.c_int, [_vp, _OP, _u64, _u64, _u64, _vp, _vp, _vp]),
     "mcb_nested_async": (C.c_int, [_vp, _OP, _u64, _u64, _u64, _u64, C.c_int, _vp, _vp, _vp, _vp]),
     "mcb_launch_count": (_u64, [_vp]),
+    "mcb_timing_enable": (C.c_int, [_vp, C.c_int]),
+    "mcb_timing_read": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_double), C.POINTER(_u64)]),
     "mcb_philox_blocks": (C.c_int, [_vp, _u64, _vp, _vp, _u64, _vp]),
     "mcb_curand_blocks": (C.c_int, [_vp, _u64, _vp, _vp, _u64, _vp]),
     "mcb_stream_normals": (C.c_int, [_vp, _u64, _u64, _u64, _u64, _vp]),
@@ -188,6 +191,16 @@ class Engine:
     @property
     def launch_count(self) -> int:
         return int(self._lib.mcb_launch_count(self._h))
+
+    def timing_enable(self, on=True):
+        _check(self._lib.mcb_timing_enable(self._h, 1 if on else 0))
+
+    def timing_read(self, kernel):
+        """(total device ms, launches) of the recorded launches of ``kernel`` since the last read."""
+        ms = C.c_double()
+        n = _u64()
+        _check(self._lib.mcb_timing_read(self._h, kernel, C.byref(ms), C.byref(n)))
+        return ms.value, int(n.value)
 
     def price_european(self, opt, n_paths=0, seed=1234, option_type=CALL) -> Result:
         out = Result()

@@ -90,6 +90,15 @@ struct mcb_engine {
     size_t h_results_cap = 0;
     double *h_segments = nullptr;          // pinned, [MCB_SEGMENTS][2] of the last whole-job call
     uint64_t launches = 0;
+    // optional per-kernel CUDA-event timing (mcb_timing_enable): one (start, stop) pair per
+    // hot-path launch, recorded on the launching stream, read back by mcb_timing_read.
+    bool timing = false;
+    struct TimedLaunch {
+        cudaEvent_t start, stop;
+        int kernel;
+    };
+    std::vector<TimedLaunch> timed;      // recorded since the last read
+    std::vector<TimedLaunch> event_pool; // recycled pairs
 };
 
 namespace {
@@ -109,6 +118,34 @@ struct DeviceGuard {
 };
 
 cudaStream_t pick(mcb_engine *e, void *stream) { return stream ? (cudaStream_t)stream : e->stream; }
+
+// Brackets one kernel launch with CUDA events on the launching stream when timing is on.
+constexpr size_t kMaxTimedLaunches = 1u << 16;
+struct TimedScope {
+    mcb_engine *e;
+    cudaStream_t st;
+    cudaEvent_t stop = nullptr;
+    TimedScope(mcb_engine *eng, int kernel, cudaStream_t stream) : e(eng), st(stream)
+    {
+        if (!e->timing || e->timed.size() >= kMaxTimedLaunches) return;
+        mcb_engine::TimedLaunch t{};
+        if (!e->event_pool.empty()) {
+            t = e->event_pool.back();
+            e->event_pool.pop_back();
+        } else if (cudaEventCreate(&t.start) != cudaSuccess || cudaEventCreate(&t.stop) != cudaSuccess) {
+            cudaGetLastError();
+            return;
+        }
+        t.kernel = kernel;
+        cudaEventRecord(t.start, st);
+        stop = t.stop;
+        e->timed.push_back(t);
+    }
+    ~TimedScope()
+    {
+        if (stop) cudaEventRecord(stop, st);
+    }
+};
 
 int check_common(const mcb_engine *e, const mcb_option_data *o)
 {
@@ -181,10 +218,13 @@ int launch_european(mcb_engine *e, const EuropeanParams &prm, int option_type, u
 {
     if (n_ctas == 0) return MCB_OK;
     if (n_ctas > 0x7fffffffull) return fail(MCB_ERR_INVALID, "too many chunks for one launch");
-    if (option_type == MCB_PUT)
-        european_kernel<kPut, PPS><<<(unsigned)n_ctas, kSlots, 0, st>>>(prm, partials, payoffs, payoffs_first);
-    else
-        european_kernel<kCall, PPS><<<(unsigned)n_ctas, kSlots, 0, st>>>(prm, partials, payoffs, payoffs_first);
+    {
+        TimedScope timed(e, MCB_KERNEL_EUROPEAN, st);
+        if (option_type == MCB_PUT)
+            european_kernel<kPut, PPS><<<(unsigned)n_ctas, kSlots, 0, st>>>(prm, partials, payoffs, payoffs_first);
+        else
+            european_kernel<kCall, PPS><<<(unsigned)n_ctas, kSlots, 0, st>>>(prm, partials, payoffs, payoffs_first);
+    }
     e->launches++;
     CU(cudaGetLastError());
     return MCB_OK;
@@ -291,6 +331,11 @@ int mcb_engine_destroy(mcb_engine *e)
         cudaStreamSynchronize(e->stream);
         cudaStreamDestroy(e->stream);
     }
+    for (auto *v : {&e->timed, &e->event_pool})
+        for (auto &t : *v) {
+            cudaEventDestroy(t.start);
+            cudaEventDestroy(t.stop);
+        }
     e->partials.release();
     e->segments.release();
     e->results.release();
@@ -325,6 +370,39 @@ int mcb_synchronize(mcb_engine *e)
 }
 
 uint64_t mcb_launch_count(mcb_engine *e) { return e ? e->launches : 0; }
+
+int mcb_timing_enable(mcb_engine *e, int on)
+{
+    if (!e) return fail(MCB_ERR_INVALID, "engine is NULL");
+    e->timing = on != 0;
+    return MCB_OK;
+}
+
+int mcb_timing_read(mcb_engine *e, int kernel, double *total_ms, uint64_t *launches)
+{
+    if (!e || !total_ms || !launches) return fail(MCB_ERR_INVALID, "NULL argument");
+    if (kernel < 0 || kernel >= MCB_KERNEL_COUNT) return fail(MCB_ERR_INVALID, "bad kernel id");
+    DeviceGuard g(e->device);
+    double ms = 0.0;
+    uint64_t n = 0;
+    std::vector<mcb_engine::TimedLaunch> keep;
+    for (const auto &t : e->timed) {
+        if (t.kernel != kernel) {
+            keep.push_back(t);
+            continue;
+        }
+        CU(cudaEventSynchronize(t.stop));
+        float one = 0.0f;
+        CU(cudaEventElapsedTime(&one, t.start, t.stop));
+        ms += (double)one;
+        ++n;
+        e->event_pool.push_back(t);
+    }
+    e->timed.swap(keep);
+    *total_ms = ms;
+    *launches = n;
+    return MCB_OK;
+}
 
 // -------------------------------------------------------------------------------- European
 int mcb_european_segments_async(mcb_engine *e, const mcb_option_data *opt, uint64_t n_paths, uint64_t seed,
@@ -436,8 +514,11 @@ int mcb_bullet_segments_async(mcb_engine *e, const mcb_option_data *opt, uint64_
     WalkParams prm;
     if ((rc = bullet_params(opt, n_paths, seed, Ik, Sk, Tk, c_lo, &prm))) return rc;
     if (c_hi > c_lo) {
-        bullet_kernel<MCB_BULLET_PATHS_PER_SLOT><<<(unsigned)(c_hi - c_lo), kSlots, 0, st>>>(prm, e->partials.ptr,
-                                                                                             nullptr, 0);
+        {
+            TimedScope timed(e, MCB_KERNEL_BULLET, st);
+            bullet_kernel<MCB_BULLET_PATHS_PER_SLOT><<<(unsigned)(c_hi - c_lo), kSlots, 0, st>>>(prm, e->partials.ptr,
+                                                                                                 nullptr, 0);
+        }
         e->launches++;
         CU(cudaGetLastError());
     }
@@ -537,14 +618,17 @@ int mcb_trajectories_async(mcb_engine *e, const mcb_option_data *opt, uint64_t f
     const bool vec = (opt->N_STEPS % 4 == 0) && ((uintptr_t)d_prices % 16 == 0) &&
                      (!d_counts || (uintptr_t)d_counts % 16 == 0);
     cudaStream_t st = pick(e, stream);
-    if (vec && d_counts)
-        trajectory_kernel<true, true><<<(unsigned)ctas, kPathWarps * 32, 0, st>>>(prm, d_prices, d_counts);
-    else if (vec)
-        trajectory_kernel<true, false><<<(unsigned)ctas, kPathWarps * 32, 0, st>>>(prm, d_prices, nullptr);
-    else if (d_counts)
-        trajectory_kernel<false, true><<<(unsigned)ctas, kPathWarps * 32, 0, st>>>(prm, d_prices, d_counts);
-    else
-        trajectory_kernel<false, false><<<(unsigned)ctas, kPathWarps * 32, 0, st>>>(prm, d_prices, nullptr);
+    {
+        TimedScope timed(e, MCB_KERNEL_TRAJECTORY, st);
+        if (vec && d_counts)
+            trajectory_kernel<true, true><<<(unsigned)ctas, kPathWarps * 32, 0, st>>>(prm, d_prices, d_counts);
+        else if (vec)
+            trajectory_kernel<true, false><<<(unsigned)ctas, kPathWarps * 32, 0, st>>>(prm, d_prices, nullptr);
+        else if (d_counts)
+            trajectory_kernel<false, true><<<(unsigned)ctas, kPathWarps * 32, 0, st>>>(prm, d_prices, d_counts);
+        else
+            trajectory_kernel<false, false><<<(unsigned)ctas, kPathWarps * 32, 0, st>>>(prm, d_prices, nullptr);
+    }
     e->launches++;
     CU(cudaGetLastError());
     return MCB_OK;
@@ -614,7 +698,11 @@ int mcb_nested_async(mcb_engine *e, const mcb_option_data *opt, uint64_t first_o
     prm.first_outer = first_outer;
     prm.keys_outer = make_philox_keys(seed_outer);
     prm.keys_inner = make_philox_keys(seed_inner);
-    nested_kernel<<<(unsigned)n_outer, kSlots, 0, pick(e, stream)>>>(prm, d_F, d_prices, d_counts);
+    {
+        cudaStream_t st = pick(e, stream);
+        TimedScope timed(e, MCB_KERNEL_NESTED, st);
+        nested_kernel<<<(unsigned)n_outer, kSlots, 0, st>>>(prm, d_F, d_prices, d_counts);
+    }
     e->launches++;
     CU(cudaGetLastError());
     return MCB_OK;

@@ -1,0 +1,108 @@
+"""Multi-GPU pricing: one process per GPU, paths sharded by index, ONE sum-allreduce.
+
+The reference is single-GPU ("Parallelism strategies: none"); this is the
+additive capability north_star asks for.  Every path is a pure function of (seed, path id), so
+rank g of G prices the chunks of its own 64/G reduction segments and writes +0.0 into the
+segments it does not own; one ``all_reduce(SUM)`` of the 1 KiB segment vector (x + 0.0 is exact,
+so the result does not depend on NCCL's ring/tree order) leaves all 64 double segments on every
+rank, and the fixed final tree (``mcb_combine_segments_async``) gives a price whose bits do not
+depend on G.  ``torch`` / ``torch.distributed`` are plumbing only: device memory, the stream,
+the NCCL communicator.  Trajectory mode and nested MC shard by contiguous path slabs with no
+collective at all (``path_span``).
+
+Nothing here imports ``oracle/``; without the CUDA library every call raises ``McbError``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+from . import (CALL, SEGMENTS, Engine, Result, path_span)  # noqa: F401  (re-exported helpers)
+
+
+class ShardedPricer:
+    """European / bullet / sweep pricing over the ranks of a ``torch.distributed`` group.
+
+    All work is enqueued on ``torch.cuda.current_stream()`` of this rank's device: kernel ->
+    all_reduce -> final tree, with no host synchronisation in between.  The C-ABI reads a NULL
+    stream as "the engine's own stream", so callers must make a real (non-default) torch stream
+    current -- ``with torch.cuda.stream(pricer.stream):`` -- before enqueueing.
+    """
+
+    def __init__(self, engine: Engine, group=None, max_sets: int = 1):
+        import torch
+        import torch.distributed as dist
+
+        self.torch = torch
+        self.dist = dist
+        self.engine = engine
+        self.group = group
+        if dist.is_available() and dist.is_initialized():
+            self.rank = dist.get_rank(group)
+            self.world = dist.get_world_size(group)
+        else:
+            self.rank, self.world = 0, 1
+        self.device = torch.device("cuda", engine.device)
+        self.stream = torch.cuda.Stream(self.device)
+        self._reserve(max_sets)
+
+    def _reserve(self, n_sets: int):
+        t = self.torch
+        self.max_sets = n_sets
+        self.segments = t.zeros(n_sets * 2 * SEGMENTS, dtype=t.float64, device=self.device)
+        self.results = t.zeros(n_sets * 5, dtype=t.float64, device=self.device)      # mcb_result = 40 bytes
+        self.h_results = t.zeros(n_sets * 5, dtype=t.float64).pin_memory()
+
+    def _stream(self):
+        ptr = self.torch.cuda.current_stream(self.device).cuda_stream
+        if not ptr:
+            raise RuntimeError("the legacy default stream is current: wrap the call in "
+                               "`with torch.cuda.stream(pricer.stream):`")
+        return ptr
+
+    def _finish_async(self, n_sets, n_paths, r, T):
+        if self.world > 1:
+            self.dist.all_reduce(self.segments[: n_sets * 2 * SEGMENTS], op=self.dist.ReduceOp.SUM, group=self.group)
+        self.engine.combine_segments_async(self.segments.data_ptr(), n_sets, n_paths, r, T,
+                                           self.results.data_ptr(), self._stream())
+
+    # ---- enqueue-only (device-resident result in self.results) ---------------------------
+    def european_async(self, opt, n_paths, seed=1234, option_type=CALL):
+        self.engine.european_segments_async(opt, n_paths, seed, option_type, self.rank, self.world,
+                                            self.segments.data_ptr(), self._stream())
+        self._finish_async(1, n_paths, opt.r, opt.T)
+
+    def bullet_async(self, opt, n_paths, seed=1234, Ik=0, Sk=0.0, Tk=0):
+        self.engine.bullet_segments_async(opt, n_paths, seed, Ik, Sk, Tk, self.rank, self.world,
+                                          self.segments.data_ptr(), self._stream())
+        self._finish_async(1, n_paths, opt.r, opt.T)
+
+    def sweep_async(self, opt, strikes, vols, n_paths, seed=1234, option_type=CALL):
+        n_sets = len(strikes)
+        if n_sets > self.max_sets:
+            self._reserve(n_sets)
+        self.engine.sweep_segments_async(opt, strikes, vols, n_paths, seed, option_type, self.rank, self.world,
+                                         self.segments.data_ptr(), self._stream())
+        self._finish_async(n_sets, n_paths, opt.r, opt.T)
+
+    # ---- synchronous: result on the host ------------------------------------------------
+    def _fetch(self, n_sets):
+        self.h_results[: n_sets * 5].copy_(self.results[: n_sets * 5], non_blocking=True)
+        self.torch.cuda.current_stream(self.device).synchronize()
+        out = (Result * n_sets)()
+        C.memmove(out, self.h_results.data_ptr(), C.sizeof(Result) * n_sets)
+        return list(out)
+
+    def price_european(self, opt, n_paths, seed=1234, option_type=CALL) -> Result:
+        with self.torch.cuda.stream(self.stream):
+            self.european_async(opt, n_paths, seed, option_type)
+            return self._fetch(1)[0]
+
+    def price_bullet(self, opt, n_paths, seed=1234, Ik=0, Sk=0.0, Tk=0) -> Result:
+        with self.torch.cuda.stream(self.stream):
+            self.bullet_async(opt, n_paths, seed, Ik, Sk, Tk)
+            return self._fetch(1)[0]
+
+    def price_sweep(self, opt, strikes, vols, n_paths, seed=1234, option_type=CALL):
+        with self.torch.cuda.stream(self.stream):
+            self.sweep_async(opt, strikes, vols, n_paths, seed, option_type)
+            return self._fetch(len(strikes))
