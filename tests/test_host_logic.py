@@ -141,6 +141,7 @@ def test_product_never_imports_oracle():
                 assert "import oracle" not in text and "from oracle" not in text, f
                 assert not any("#include" in ln and "oracle" in ln for ln in text.splitlines()), f
                 assert "libmc_oracle" not in text, f
-    for f in os.listdir(os.path.join(ROOT, "include")):
-        text = open(os.path.join(ROOT, "include", f)).read()
-        assert not any("#include" in ln and "oracle" in ln for ln in text.splitlines()), f
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "include")):
+        for f in files:
+            text = open(os.path.join(dirpath, f)).read()
+            assert not any("#include" in ln and "oracle" in ln for ln in text.splitlines()), f
