@@ -86,6 +86,7 @@ struct mcb_engine {
     DeviceBuffer<double> segments;
     DeviceBuffer<ResultDev> results;
     DeviceBuffer<unsigned char> scratch;   // hooks / host<->device staging
+    DeviceBuffer<float> nested_ws;         // nested MC: log2 S, (prices), (counts) of the outer points
     mcb_result *h_results = nullptr;       // pinned
     size_t h_results_cap = 0;
     double *h_segments = nullptr;          // pinned, [MCB_SEGMENTS][2] of the last whole-job call
@@ -340,6 +341,7 @@ int mcb_engine_destroy(mcb_engine *e)
     e->segments.release();
     e->results.release();
     e->scratch.release();
+    e->nested_ws.release();
     if (e->h_results) cudaFreeHost(e->h_results);
     if (e->h_segments) cudaFreeHost(e->h_segments);
     delete e;
@@ -597,8 +599,8 @@ int mcb_price_sweep(mcb_engine *e, const mcb_option_data *opt, const float *stri
 }
 
 // ------------------------------------------------------------------------------ trajectories
-int mcb_trajectories_async(mcb_engine *e, const mcb_option_data *opt, uint64_t first_path, uint64_t n_paths,
-                           uint64_t seed, float *d_prices, int *d_counts, void *stream)
+static int trajectories_launch(mcb_engine *e, const mcb_option_data *opt, uint64_t first_path, uint64_t n_paths,
+                               uint64_t seed, float *d_prices, int *d_counts, float *d_logs, void *stream)
 {
     int rc = check_common(e, opt);
     if (rc) return rc;
@@ -613,25 +615,39 @@ int mcb_trajectories_async(mcb_engine *e, const mcb_option_data *opt, uint64_t f
     prm.first_path = first_path;
     prm.n_paths = n_paths;
     prm.keys = make_philox_keys(seed);
-    const uint64_t ctas = (n_paths + (uint64_t)kPathWarps * 32 - 1) / ((uint64_t)kPathWarps * 32);
+    const uint64_t rows_per_cta = (uint64_t)kPathWarps * kPathsPerWarp;
+    const uint64_t ctas = (n_paths + rows_per_cta - 1) / rows_per_cta;
     if (ctas > 0x7fffffffull) return fail(MCB_ERR_INVALID, "too many paths for one launch");
     const bool vec = (opt->N_STEPS % 4 == 0) && ((uintptr_t)d_prices % 16 == 0) &&
-                     (!d_counts || (uintptr_t)d_counts % 16 == 0);
+                     (!d_counts || (uintptr_t)d_counts % 16 == 0) && (!d_logs || (uintptr_t)d_logs % 16 == 0);
+    const bool wide = opt->N_STEPS > 128;  // 8 steps per lane (two Philox blocks) for long rows
     cudaStream_t st = pick(e, stream);
     {
         TimedScope timed(e, MCB_KERNEL_TRAJECTORY, st);
-        if (vec && d_counts)
-            trajectory_kernel<true, true><<<(unsigned)ctas, kPathWarps * 32, 0, st>>>(prm, d_prices, d_counts);
-        else if (vec)
-            trajectory_kernel<true, false><<<(unsigned)ctas, kPathWarps * 32, 0, st>>>(prm, d_prices, nullptr);
-        else if (d_counts)
-            trajectory_kernel<false, true><<<(unsigned)ctas, kPathWarps * 32, 0, st>>>(prm, d_prices, d_counts);
-        else
-            trajectory_kernel<false, false><<<(unsigned)ctas, kPathWarps * 32, 0, st>>>(prm, d_prices, nullptr);
+        const unsigned g = (unsigned)ctas, b = kPathWarps * 32;
+#define MCB_TRAJ(SPL, VEC, CNT) trajectory_kernel<SPL, VEC, CNT><<<g, b, 0, st>>>(prm, d_prices, d_counts, d_logs)
+        if (wide) {
+            if (vec && d_counts) MCB_TRAJ(8, true, true);
+            else if (vec) MCB_TRAJ(8, true, false);
+            else if (d_counts) MCB_TRAJ(8, false, true);
+            else MCB_TRAJ(8, false, false);
+        } else {
+            if (vec && d_counts) MCB_TRAJ(4, true, true);
+            else if (vec) MCB_TRAJ(4, true, false);
+            else if (d_counts) MCB_TRAJ(4, false, true);
+            else MCB_TRAJ(4, false, false);
+        }
+#undef MCB_TRAJ
     }
     e->launches++;
     CU(cudaGetLastError());
     return MCB_OK;
+}
+
+int mcb_trajectories_async(mcb_engine *e, const mcb_option_data *opt, uint64_t first_path, uint64_t n_paths,
+                           uint64_t seed, float *d_prices, int *d_counts, void *stream)
+{
+    return trajectories_launch(e, opt, first_path, n_paths, seed, d_prices, d_counts, nullptr, stream);
 }
 
 int mcb_simulate_trajectories(mcb_engine *e, const mcb_option_data *opt, uint64_t first_path, uint64_t n_paths,
@@ -687,21 +703,30 @@ int mcb_nested_async(mcb_engine *e, const mcb_option_data *opt, uint64_t first_o
     if (n_outer == 0) return MCB_OK;
     if (n_outer > 0x7fffffffull) return fail(MCB_ERR_INVALID, "too many outer paths for one launch");
     DeviceGuard g(e->device);
+    // outer walk: trajectory_kernel, which also leaves log2 S and the barrier count of every
+    // point in the engine's workspace (prices / counts go to the caller's buffers when given)
+    const size_t n = (size_t)n_outer * (size_t)opt->N_STEPS;
+    const size_t n4 = (n + 3) & ~(size_t)3;  // keeps every sub-buffer 16-byte aligned
+    if ((rc = e->nested_ws.reserve(n4 * 3))) return rc;
+    float *ws_logs = e->nested_ws.ptr;
+    float *ws_prices = d_prices ? d_prices : e->nested_ws.ptr + n4;
+    int *ws_counts = d_counts ? d_counts : reinterpret_cast<int *>(e->nested_ws.ptr + 2 * n4);
+    if ((rc = trajectories_launch(e, opt, first_outer, n_outer, seed_outer, ws_prices, ws_counts, ws_logs, stream)))
+        return rc;
     const WalkConsts w = walk_consts(opt, (double)opt->S0);
     NestedParams prm{};
-    prm.l0 = w.l0; prm.dz = w.dz; prm.v = w.v; prm.lB = w.lB;
+    prm.dz = w.dz; prm.v = w.v; prm.lB = w.lB;
     prm.K = opt->K; prm.P1 = opt->P1; prm.P2 = opt->P2;
     prm.n_steps = opt->N_STEPS;
     prm.n_inner = opt->N_PATHS_INNER;
     prm.discount_mode = discount_mode;
     prm.r = opt->r; prm.T = opt->T; prm.dt = opt->step;
     prm.first_outer = first_outer;
-    prm.keys_outer = make_philox_keys(seed_outer);
     prm.keys_inner = make_philox_keys(seed_inner);
     {
         cudaStream_t st = pick(e, stream);
         TimedScope timed(e, MCB_KERNEL_NESTED, st);
-        nested_kernel<<<(unsigned)n_outer, kSlots, 0, st>>>(prm, d_F, d_prices, d_counts);
+        nested_kernel<<<(unsigned)n_outer, kSlots, 0, st>>>(prm, ws_logs, ws_counts, d_F);
     }
     e->launches++;
     CU(cudaGetLastError());

@@ -349,11 +349,13 @@ def test_trajectories_are_independent_of_the_launch_slab(engine, pkg):
 
 def test_trajectory_terminal_matches_bullet_walk(engine, pkg):
     """The last stored price of path p and the bullet kernel's terminal payoff come from the same
-    normals in the same FP32 order: payoff == max(S_T - K, 0) when the gate is open."""
+    normals; the trajectory kernel sums the log2 increments by in-lane prefix + warp scan, the
+    bullet kernel serially, so they agree to FP32 rounding of a 100-term sum (~5e-6 relative,
+    i.e. < 2e-3 absolute on prices ~100-200)."""
     kw = dict(S0=100.0, K=100.0, T=1.0, r=0.05, v=0.2, B=0.0, P1=0, P2=1000, N_STEPS=100, N_PATHS=2048)
     prices = engine.simulate_trajectories(pkg.option(**kw), 0, 2048, 1234)
     pay = engine.bullet_payoffs(pkg.option(**kw), 0, 2048, 1234)
-    assert np.allclose(pay, np.maximum(prices[:, -1] - 100.0, 0.0), rtol=0, atol=1e-4)
+    assert np.allclose(pay, np.maximum(prices[:, -1] - 100.0, 0.0), rtol=0, atol=2e-3)
 
 
 def test_trajectories_device_buffer_full_size(engine, pkg):
