@@ -48,6 +48,7 @@ int fail(int code, const char *fmt, ...)
     } while (0)
 
 constexpr double kLog2e = 1.4426950408889634074;
+constexpr double kSqrt2Ln2d = 1.1774100225154746910;  // sqrt(2 ln 2), see philox.cuh bm_radius_unscaled
 
 template <typename T>
 struct DeviceBuffer {
@@ -175,7 +176,7 @@ EuropeanParams european_params(const mcb_option_data *o, float K, float sigma, u
     EuropeanParams p{};
     const double S0 = o->S0, r = o->r, sig = sigma, T = o->T;
     p.c0 = (float)(std::log2(S0) + (r - 0.5 * sig * sig) * T * kLog2e);
-    p.c1 = (float)(sig * std::sqrt(T) * kLog2e);
+    p.c1 = (float)(sig * std::sqrt(T) * kLog2e * kSqrt2Ln2d);  // times the UNSCALED Box-Muller radius
     p.K = K;
     p.n_paths = n_paths_end;
     p.first_chunk = first_chunk;
@@ -184,7 +185,7 @@ EuropeanParams european_params(const mcb_option_data *o, float K, float sigma, u
 }
 
 struct WalkConsts {
-    float l0, dz, v, lB;
+    float l0, sc, dr, v, lB;
 };
 
 WalkConsts walk_consts(const mcb_option_data *o, double start)
@@ -192,7 +193,8 @@ WalkConsts walk_consts(const mcb_option_data *o, double start)
     WalkConsts w;
     const double r = o->r, sig = o->v, dt = o->step;
     w.l0 = (float)std::log2(start);
-    w.dz = (float)((r - 0.5 * sig * sig) * std::sqrt(dt) / sig);
+    w.sc = (float)(sig * std::sqrt(dt) * kLog2e * kSqrt2Ln2d);
+    w.dr = (float)((r - 0.5 * sig * sig) * dt * kLog2e);
     w.v = (float)(sig * std::sqrt(dt) * kLog2e);
     w.lB = o->B > 0.0f ? (float)std::log2((double)o->B) : -INFINITY;
     return w;
@@ -485,7 +487,7 @@ static int bullet_params(const mcb_option_data *opt, uint64_t n_paths_end, uint6
     // Sk == 0 means "start from S0" exactly as inc/trajectories.cuh:141
     const WalkConsts w = walk_consts(opt, Sk == 0.0f ? (double)opt->S0 : (double)Sk);
     WalkParams p{};
-    p.l0 = w.l0; p.dz = w.dz; p.v = w.v; p.lB = w.lB;
+    p.l0 = w.l0; p.sc = w.sc; p.dr = w.dr; p.lB = w.lB;
     p.K = opt->K; p.P1 = opt->P1; p.P2 = opt->P2;
     p.n_steps = opt->N_STEPS - Tk;
     p.count0 = Ik;
@@ -610,7 +612,7 @@ static int trajectories_launch(mcb_engine *e, const mcb_option_data *opt, uint64
     DeviceGuard g(e->device);
     const WalkConsts w = walk_consts(opt, (double)opt->S0);
     PathParams prm{};
-    prm.l0 = w.l0; prm.dz = w.dz; prm.v = w.v; prm.lB = w.lB;
+    prm.l0 = w.l0; prm.sc = w.sc; prm.dr = w.dr; prm.lB = w.lB;
     prm.n_steps = opt->N_STEPS;
     prm.first_path = first_path;
     prm.n_paths = n_paths;
@@ -715,7 +717,7 @@ int mcb_nested_async(mcb_engine *e, const mcb_option_data *opt, uint64_t first_o
         return rc;
     const WalkConsts w = walk_consts(opt, (double)opt->S0);
     NestedParams prm{};
-    prm.dz = w.dz; prm.v = w.v; prm.lB = w.lB;
+    prm.sc = w.sc; prm.dr = w.dr; prm.lB = w.lB;
     prm.K = opt->K; prm.P1 = opt->P1; prm.P2 = opt->P2;
     prm.n_steps = opt->N_STEPS;
     prm.n_inner = opt->N_PATHS_INNER;
@@ -831,7 +833,7 @@ int mcb_price_from_normals(mcb_engine *e, const mcb_option_data *opt, const floa
         dp = base + nz;
     }
     const uint64_t ctas = (n_paths + kSlots - 1) / kSlots;
-    pregen_kernel<<<(unsigned)ctas, kSlots, 0, e->stream>>>(dz, n_paths, n_steps, w.l0, w.dz, w.v, opt->K, dp);
+    pregen_kernel<<<(unsigned)ctas, kSlots, 0, e->stream>>>(dz, n_paths, n_steps, w.l0, w.dr, w.v, opt->K, dp);
     e->launches++;
     CU(cudaGetLastError());
     if (where == MCB_HOST)

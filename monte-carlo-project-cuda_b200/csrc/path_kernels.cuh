@@ -30,7 +30,7 @@ namespace mcb {
 // on which launch, slab or GPU produced it.
 // ------------------------------------------------------------------------------------------
 struct PathParams {
-    float l0, dz, v, lB;
+    float l0, sc, dr, lB;   // sc, dr: see WalkParams
     int n_steps;
     uint32_t pad;
     uint64_t first_path;
@@ -41,18 +41,52 @@ struct PathParams {
 constexpr int kPathWarps = 8;     // warps (= rows in flight) per CTA
 constexpr int kPathsPerWarp = 8;  // rows a warp walks one after the other
 
-// exclusive prefix over the lanes of a warp (lane 0 gets 0) and the warp total
-template <typename T>
-__device__ __forceinline__ T warp_exclusive_scan(T x, int lane, T &total)
+// One stage of an inclusive warp scan: x += (value of lane - off), when that lane exists.
+// shfl.sync.up hands back the "source lane in range" predicate, so a stage is SHFL + one
+// predicated add (the C++ intrinsic costs SHFL + FADD + FSEL).
+__device__ __forceinline__ float scan_stage(float x, int off)
 {
+    asm("{ .reg .f32 t; .reg .pred p;\n\t"
+        "shfl.sync.up.b32 t|p, %0, %1, 0, 0xffffffff;\n\t"
+        "@p add.f32 %0, %0, t; }"
+        : "+f"(x) : "r"(off));
+    return x;
+}
+__device__ __forceinline__ int scan_stage(int x, int off)
+{
+    asm("{ .reg .b32 t; .reg .pred p;\n\t"
+        "shfl.sync.up.b32 t|p, %0, %1, 0, 0xffffffff;\n\t"
+        "@p add.s32 %0, %0, t; }"
+        : "+r"(x) : "r"(off));
+    return x;
+}
+// value of the lane below (0 for lane 0)
+__device__ __forceinline__ float shift_up_one(float x)
+{
+    float r;
+    asm("{ .reg .pred p;\n\t"
+        "shfl.sync.up.b32 %0|p, %1, 1, 0, 0xffffffff;\n\t"
+        "@!p mov.f32 %0, 0f00000000; }"
+        : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ int shift_up_one(int x)
+{
+    int r;
+    asm("{ .reg .pred p;\n\t"
+        "shfl.sync.up.b32 %0|p, %1, 1, 0, 0xffffffff;\n\t"
+        "@!p mov.b32 %0, 0; }"
+        : "=r"(r) : "r"(x));
+    return r;
+}
+// exclusive prefix over the lanes of a warp (lane 0 gets 0): 6 SHFL + 5 adds
+template <typename T>
+__device__ __forceinline__ T warp_exclusive_scan(T x)
+{
+    x = shift_up_one(x);
 #pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-        const T y = __shfl_up_sync(kFullMask, x, off);
-        if (lane >= off) x = x + y;
-    }
-    total = __shfl_sync(kFullMask, x, 31);
-    const T up = __shfl_up_sync(kFullMask, x, 1);
-    return lane ? up : T(0);
+    for (int off = 1; off < 32; off <<= 1) x = scan_stage(x, off);
+    return x;
 }
 
 // SPL = steps per lane (4: one Philox block, 8: two).  VEC4: rows are 16-byte aligned
@@ -66,38 +100,38 @@ trajectory_kernel(const __grid_constant__ PathParams prm, float *__restrict__ pr
     constexpr int kBlocks = SPL / 4;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n_steps = prm.n_steps;
-    const uint64_t row0 = ((uint64_t)blockIdx.x * kPathWarps + warp) * kPathsPerWarp;
+    // launch-local row indices fit 32 bits (the host caps a launch at 2^31 rows)
+    const uint32_t n_rows = (uint32_t)prm.n_paths;
+    uint32_t row = (blockIdx.x * kPathWarps + warp) * kPathsPerWarp;
+    const uint32_t row_end = min(row + (uint32_t)kPathsPerWarp, n_rows);
+    const int lane_step = SPL * lane;
 
 #pragma unroll 1
-    for (int r = 0; r < kPathsPerWarp; ++r) {
-        const uint64_t row = row0 + r;
-        if (row >= prm.n_paths) return;
+    for (; row < row_end; ++row) {
         const uint64_t p = prm.first_path + row;
         const uint32_t p_lo = (uint32_t)p, p_hi = (uint32_t)(p >> 32);
-        const uint64_t row_off = row * (uint64_t)n_steps;
+        const uint64_t row_off = (uint64_t)row * (uint32_t)n_steps + (uint32_t)lane_step;
+        float *out_p = prices + row_off;
+        int *out_c = COUNTS ? counts + row_off : nullptr;
+        float *out_l = logs ? logs + row_off : nullptr;
         float carry_l = prm.l0;
         int carry_c = 0;
 
 #pragma unroll 1
         for (int step0 = 0; step0 < n_steps; step0 += 32 * SPL) {
-            const int my_step = step0 + SPL * lane;
-            float a[SPL];  // in-lane inclusive prefix of the log2 increments
-            if (my_step < n_steps) {
-                float z[SPL];
+            const int my_step = step0 + lane_step;
+            const bool active = my_step < n_steps;
+            // Branch-free on purpose: lanes past the end of the row (only ever the tail lanes of
+            // the last pass) compute and discard, which keeps the warp converged for the shuffles.
+            float a[SPL];  // log2 increments, then their in-lane inclusive prefix
 #pragma unroll
-                for (int b = 0; b < kBlocks; ++b)
-                    normals4(philox4x32_10((uint32_t)(my_step >> 2) + b, 0u, p_lo, p_hi, prm.keys), prm.dz, z + 4 * b);
-                a[0] = prm.v * z[0];
+            for (int b = 0; b < kBlocks; ++b)
+                increments4(philox4x32_10((uint32_t)(my_step >> 2) + b, 0u, p_lo, p_hi, prm.keys), prm.sc, prm.dr,
+                            a + 4 * b);
 #pragma unroll
-                for (int j = 1; j < SPL; ++j) a[j] = fmaf(prm.v, z[j], a[j - 1]);
-            } else {
-#pragma unroll
-                for (int j = 0; j < SPL; ++j) a[j] = 0.0f;
-            }
-            float total;
-            const float base = carry_l + warp_exclusive_scan(a[SPL - 1], lane, total);
-            carry_l = carry_l + total;
-
+            for (int j = 1; j < SPL; ++j) a[j] = a[j] + a[j - 1];
+            const float lane_total = active ? a[SPL - 1] : 0.0f;
+            const float base = carry_l + warp_exclusive_scan(lane_total);
             float s[SPL];
             int c[SPL];
 #pragma unroll
@@ -105,6 +139,7 @@ trajectory_kernel(const __grid_constant__ PathParams prm, float *__restrict__ pr
                 a[j] = base + a[j];
                 s[j] = mufu_ex2(a[j]);
             }
+            carry_l = __shfl_sync(kFullMask, base + lane_total, 31);
             if (COUNTS) {
                 int run = 0;
 #pragma unroll
@@ -112,26 +147,24 @@ trajectory_kernel(const __grid_constant__ PathParams prm, float *__restrict__ pr
                     run += (a[j] < prm.lB && my_step + j < n_steps) ? 1 : 0;
                     c[j] = run;
                 }
-                int ctotal;
-                const int cbase = carry_c + warp_exclusive_scan(run, lane, ctotal);
-                carry_c += ctotal;
+                const int cbase = carry_c + warp_exclusive_scan(run);
 #pragma unroll
                 for (int j = 0; j < SPL; ++j) c[j] += cbase;
+                carry_c = __shfl_sync(kFullMask, c[SPL - 1], 31);
             }
 
-            if (my_step < n_steps) {
-                const uint64_t off = row_off + (uint64_t)my_step;
+            if (active) {
                 if (VEC4) {  // n_steps % 4 == 0: whole float4s are in range
 #pragma unroll
                     for (int b = 0; b < kBlocks; ++b) {
-                        if (my_step + 4 * b < n_steps) {
-                            __stcs(reinterpret_cast<float4 *>(prices + off) + b,
+                        if (b == 0 || my_step + 4 * b < n_steps) {
+                            __stcs(reinterpret_cast<float4 *>(out_p + step0) + b,
                                    make_float4(s[4 * b], s[4 * b + 1], s[4 * b + 2], s[4 * b + 3]));
                             if (COUNTS)
-                                __stcs(reinterpret_cast<int4 *>(counts + off) + b,
+                                __stcs(reinterpret_cast<int4 *>(out_c + step0) + b,
                                        make_int4(c[4 * b], c[4 * b + 1], c[4 * b + 2], c[4 * b + 3]));
                             if (logs)
-                                __stcs(reinterpret_cast<float4 *>(logs + off) + b,
+                                __stcs(reinterpret_cast<float4 *>(out_l + step0) + b,
                                        make_float4(a[4 * b], a[4 * b + 1], a[4 * b + 2], a[4 * b + 3]));
                         }
                     }
@@ -139,9 +172,9 @@ trajectory_kernel(const __grid_constant__ PathParams prm, float *__restrict__ pr
 #pragma unroll
                     for (int j = 0; j < SPL; ++j) {
                         if (my_step + j < n_steps) {
-                            __stcs(prices + off + j, s[j]);
-                            if (COUNTS) __stcs(counts + off + j, c[j]);
-                            if (logs) __stcs(logs + off + j, a[j]);
+                            __stcs(out_p + step0 + j, s[j]);
+                            if (COUNTS) __stcs(out_c + step0 + j, c[j]);
+                            if (logs) __stcs(out_l + step0 + j, a[j]);
                         }
                     }
                 }
@@ -161,7 +194,7 @@ trajectory_kernel(const __grid_constant__ PathParams prm, float *__restrict__ pr
 // RESTARTS from the point's state (the reference carries state over, inc/nmc.cuh:51-53).
 // ------------------------------------------------------------------------------------------
 struct NestedParams {
-    float dz, v, lB, K;
+    float sc, dr, lB, K;   // sc, dr: see WalkParams
     int P1, P2, n_steps, n_inner;
     int discount_mode;     // MCB_DISCOUNT_*
     float r, T, dt;
@@ -191,7 +224,7 @@ nested_kernel(const __grid_constant__ NestedParams prm, const float *__restrict_
                 const uint64_t sub = q + (uint64_t)jj;
                 float l = lo;
                 int c = co;
-                walk_path(l, c, (uint32_t)sub, (uint32_t)(sub >> 32), remaining, prm.dz, prm.v, prm.lB,
+                walk_path(l, c, (uint32_t)sub, (uint32_t)(sub >> 32), remaining, prm.sc, prm.dr, prm.lB,
                           prm.keys_inner);
                 const float pay = (c >= prm.P1 && c <= prm.P2) ? fmaxf(mufu_ex2(l) - prm.K, 0.0f) : 0.0f;
                 sum = sum + pay;

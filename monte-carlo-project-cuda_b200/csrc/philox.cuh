@@ -110,13 +110,16 @@ __device__ __forceinline__ float mufu_cos(float x)
 
 constexpr float k2Pow32Inv = 2.3283064e-10f;                 // CURAND_2POW32_INV
 constexpr float k2Pow32Inv2Pi = 2.3283064e-10f * 6.2831855f; // CURAND_2POW32_INV_2PI
-constexpr float kMinus2Ln2 = -1.3862943611198906f;           // -2 ln 2
+constexpr float kSqrt2Ln2 = 1.1774100225154747f;             // sqrt(2 ln 2)
 
-// s = sqrt(-2 ln u) : I2FP, FFMA, MUFU.LG2, FMUL, MUFU.SQRT
-__device__ __forceinline__ float bm_radius(uint32_t x)
+// Unscaled Box-Muller radius t = sqrt(-log2 u), so that s = sqrt(-2 ln u) = sqrt(2 ln 2) * t.
+// The constant is never applied on its own: callers fold it into the scale they multiply the
+// normal by anyway (sigma sqrt(dt) log2 e ...), which removes one FMUL per pair; the negation
+// rides on the MUFU.SQRT operand.  I2FP, FFMA, MUFU.LG2, MUFU.SQRT.
+__device__ __forceinline__ float bm_radius_unscaled(uint32_t x)
 {
     const float u = fmaf(__uint2float_rn(x), k2Pow32Inv, 0.5f * k2Pow32Inv);
-    return mufu_sqrt(kMinus2Ln2 * mufu_lg2(u));
+    return mufu_sqrt(-mufu_lg2(u));
 }
 
 // v in [-pi, pi) : I2FP, FFMA
@@ -125,23 +128,25 @@ __device__ __forceinline__ float bm_angle(uint32_t y)
     return fmaf(__int2float_rn((int)y), k2Pow32Inv2Pi, 0.5f * k2Pow32Inv2Pi);
 }
 
-// normal 0 of a Philox block (the even, "sin" member of the first pair)
-__device__ __forceinline__ float normal_sin(uint32_t x, uint32_t y)
+// normal 0 of a Philox block (the even, "sin" member of the first pair) divided by sqrt(2 ln 2)
+__device__ __forceinline__ float unit_normal_sin(uint32_t x, uint32_t y)
 {
-    return bm_radius(x) * mufu_sin(bm_angle(y));
+    return bm_radius_unscaled(x) * mufu_sin(bm_angle(y));
 }
 
-// all four normals of a Philox block, in curand_normal order, each shifted by `shift`:
-// z[j] = normal_j + shift.  Multi-step walks pass shift = drift/vol so that one FFMA per step
-// (l += vol * z) applies drift and diffusion together; shift = 0 gives the plain normals.
-__device__ __forceinline__ void normals4(const Words4 &w, float shift, float z[4])
+// The four normals of a Philox block, in curand_normal order, as affine images
+//   d[j] = scale * normal_j / sqrt(2 ln 2) + shift.
+// Multi-step walks pass scale = sigma sqrt(dt) log2(e) sqrt(2 ln 2) and shift = the per-step
+// drift in log2 units, so d[j] IS the log2-price increment of step j and a step costs one FADD;
+// scale = sqrt(2 ln 2), shift = 0 gives the plain normals.
+__device__ __forceinline__ void increments4(const Words4 &w, float scale, float shift, float d[4])
 {
-    const float s0 = bm_radius(w.x), v0 = bm_angle(w.y);
-    const float s1 = bm_radius(w.z), v1 = bm_angle(w.w);
-    z[0] = fmaf(s0, mufu_sin(v0), shift);
-    z[1] = fmaf(s0, mufu_cos(v0), shift);
-    z[2] = fmaf(s1, mufu_sin(v1), shift);
-    z[3] = fmaf(s1, mufu_cos(v1), shift);
+    const float t0 = bm_radius_unscaled(w.x) * scale, v0 = bm_angle(w.y);
+    const float t1 = bm_radius_unscaled(w.z) * scale, v1 = bm_angle(w.w);
+    d[0] = fmaf(t0, mufu_sin(v0), shift);
+    d[1] = fmaf(t0, mufu_cos(v0), shift);
+    d[2] = fmaf(t1, mufu_sin(v1), shift);
+    d[3] = fmaf(t1, mufu_cos(v1), shift);
 }
 
 }  // namespace mcb

@@ -20,8 +20,9 @@ enum { kCall = 0, kPut = 1 };
 // ------------------------------------------------------------------------------------------
 // European option, one GBM step, canonical (seed, path id) keying.
 //   St = S0 exp((r - sigma^2/2) T + sigma sqrt(T) G)  ->  St = 2^(c0 + c1 z)
-// with c0 = log2 S0 + (r - sigma^2/2) T log2 e and c1 = sigma sqrt(T) log2 e folded on the
-// host, so a path is: Philox (block 0) -> Box-Muller sin branch -> FFMA -> MUFU.EX2 -> payoff.
+// with c0 = log2 S0 + (r - sigma^2/2) T log2 e and c1 = sigma sqrt(T) log2 e sqrt(2 ln 2) (the
+// Box-Muller radius comes unscaled, philox.cuh) folded on the host, so a path is:
+// Philox (block 0) -> Box-Muller sin branch -> FFMA -> MUFU.EX2 -> payoff.
 // ------------------------------------------------------------------------------------------
 struct EuropeanParams {
     float c0, c1, K;
@@ -35,8 +36,7 @@ template <int TYPE>
 __device__ __forceinline__ float european_payoff(uint32_t p_lo, uint32_t p_hi, const EuropeanParams &prm)
 {
     const Words4 w = philox4x32_10(0u, 0u, p_lo, p_hi, prm.keys);
-    const float z = normal_sin(w.x, w.y);
-    const float St = mufu_ex2(fmaf(prm.c1, z, prm.c0));
+    const float St = mufu_ex2(fmaf(prm.c1, unit_normal_sin(w.x, w.y), prm.c0));
     return TYPE == kPut ? fmaxf(prm.K - St, 0.0f) : fmaxf(St - prm.K, 0.0f);
 }
 
@@ -80,15 +80,15 @@ european_kernel(const __grid_constant__ EuropeanParams prm, float2 *__restrict__
 }
 
 // ------------------------------------------------------------------------------------------
-// Multi-step GBM walk in log2 space, fused drift + diffusion: with dz = drift/vol folded
-// into the normal (z' = z + dz, the FFMA that scales the Box-Muller radius anyway) a step is
-// ONE FFMA, l += v z'; the barrier test is l < log2 B; one MUFU.EX2 at the end.  One Philox
-// block feeds four steps.
+// Multi-step GBM walk in log2 space, fused drift + diffusion: the FFMA that scales the
+// Box-Muller radius by the trig value anyway also applies the volatility and adds the drift
+// (increments4), so a step is ONE FADD, l += d; the barrier test is l < log2 B; one MUFU.EX2 at
+// the end.  One Philox block feeds four steps.
 // ------------------------------------------------------------------------------------------
 struct WalkParams {
     float l0;      // log2 of the start price
-    float dz;      // drift / vol = (r - sigma^2/2) sqrt(dt) / sigma
-    float v;       // sigma sqrt(dt) log2 e   (> 0)
+    float sc;      // sigma sqrt(dt) log2(e) sqrt(2 ln 2): scale of the unscaled Box-Muller radius (> 0)
+    float dr;      // (r - sigma^2/2) dt log2(e): drift per step in log2 units
     float lB;      // log2 B  (-inf when B <= 0: the barrier is never hit)
     float K;
     int P1, P2;
@@ -103,26 +103,26 @@ struct WalkParams {
 // Walk `n_steps` steps of stream (keys, subsequence) from (l, count); normal i of the stream
 // drives step i.
 __device__ __forceinline__ void walk_path(float &l, int &count, uint32_t s_lo, uint32_t s_hi, int n_steps,
-                                          float dz, float v, float lB, const PhiloxKeys &keys)
+                                          float sc, float dr, float lB, const PhiloxKeys &keys)
 {
     const int full = n_steps >> 2;
     for (int b = 0; b < full; ++b) {
-        float z[4];
-        normals4(philox4x32_10((uint32_t)b, 0u, s_lo, s_hi, keys), dz, z);
+        float d[4];
+        increments4(philox4x32_10((uint32_t)b, 0u, s_lo, s_hi, keys), sc, dr, d);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            l = fmaf(v, z[j], l);
+            l = l + d[j];
             count += (l < lB) ? 1 : 0;
         }
     }
     const int tail = n_steps & 3;
     if (tail) {
-        float z[4];
-        normals4(philox4x32_10((uint32_t)full, 0u, s_lo, s_hi, keys), dz, z);
+        float d[4];
+        increments4(philox4x32_10((uint32_t)full, 0u, s_lo, s_hi, keys), sc, dr, d);
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
             if (j < tail) {
-                l = fmaf(v, z[j], l);
+                l = l + d[j];
                 count += (l < lB) ? 1 : 0;
             }
         }
@@ -152,7 +152,7 @@ bullet_kernel(const __grid_constant__ WalkParams prm, float2 *__restrict__ parti
             const uint64_t p = base + local;
             float l = prm.l0;
             int count = prm.count0;
-            walk_path(l, count, (uint32_t)p, (uint32_t)(p >> 32), prm.n_steps, prm.dz, prm.v, prm.lB, prm.keys);
+            walk_path(l, count, (uint32_t)p, (uint32_t)(p >> 32), prm.n_steps, prm.sc, prm.dr, prm.lB, prm.keys);
             const float pay = bullet_payoff_from(l, count, prm);
             sum = sum + pay;
             sq = fmaf(pay, pay, sq);
@@ -242,14 +242,14 @@ reduce_sum_kernel(const float *__restrict__ x, uint64_t n, float *__restrict__ o
 
 // Pricing from pre-generated normals (inc/trajectories.cuh:14-52): thread per path.
 __global__ void __launch_bounds__(kSlots)
-pregen_kernel(const float *__restrict__ normals, uint64_t n_paths, int n_steps, float l0, float dz, float v,
+pregen_kernel(const float *__restrict__ normals, uint64_t n_paths, int n_steps, float l0, float dr, float v,
               float K, float *__restrict__ payoffs)
 {
     const uint64_t p = (uint64_t)blockIdx.x * kSlots + threadIdx.x;
     if (p >= n_paths) return;
     float l = l0;
     const float *z = normals + p * (uint64_t)n_steps;
-    for (int i = 0; i < n_steps; ++i) l = fmaf(v, z[i] + dz, l);
+    for (int i = 0; i < n_steps; ++i) l = fmaf(v, z[i], l) + dr;
     payoffs[p] = fmaxf(mufu_ex2(l) - K, 0.0f);
 }
 
@@ -271,7 +271,8 @@ __global__ void stream_normals_kernel(PhiloxKeys keys, uint64_t subseq, uint64_t
     if (i >= count) return;
     const uint64_t n = n0 + i, b = n >> 2;
     float z[4];
-    normals4(philox4x32_10((uint32_t)b, (uint32_t)(b >> 32), (uint32_t)subseq, (uint32_t)(subseq >> 32), keys), 0.0f, z);
+    increments4(philox4x32_10((uint32_t)b, (uint32_t)(b >> 32), (uint32_t)subseq, (uint32_t)(subseq >> 32), keys),
+                kSqrt2Ln2, 0.0f, z);
     out[i] = z[n & 3];
 }
 
