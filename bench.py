@@ -425,8 +425,9 @@ def other_workloads(torch, pkg, eng, hbm_gbs, peak_src):
     segs = torch.zeros(1024 * 2 * pkg.SEGMENTS, dtype=torch.float64, device="cuda")
     k, v = K.ravel().copy(), V.ravel().copy()
     t = timed(lambda: eng.sweep_segments_async(os_, k, v, 1 << 26, SEED, pkg.CALL, 0, 1, segs.data_ptr(), stream),
-              1, warm=1)
-    out["sweep_1024x2^26"] = {"path_params_per_s": 1024 * (1 << 26) / t, "ms": 1e3 * t}
+              3, warm=1)
+    out["sweep_1024x2^26"] = {"path_params_per_s": 1024 * (1 << 26) / t, "ms": 1e3 * t,
+                              "bound": "XU: one MUFU.EX2 per (path, set) -> 16/clk/SM = 4.65e12 /s"}
     return roofline_traj, out
 
 

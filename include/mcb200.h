@@ -171,7 +171,7 @@ uint64_t mcb_launch_count(mcb_engine *e);
  * mcb_timing_read waits for the recorded launches of `kernel`, returns their summed device
  * time and count, and forgets them. */
 enum { MCB_KERNEL_EUROPEAN = 0, MCB_KERNEL_BULLET = 1, MCB_KERNEL_TRAJECTORY = 2, MCB_KERNEL_NESTED = 3,
-       MCB_KERNEL_COUNT = 4 };
+       MCB_KERNEL_SWEEP = 4, MCB_KERNEL_COUNT = 5 };
 int mcb_timing_enable(mcb_engine *e, int on);
 int mcb_timing_read(mcb_engine *e, int kernel, double *total_ms, uint64_t *launches);
 

@@ -36,7 +36,7 @@ DISCOUNT_COMPAT, DISCOUNT_CORRECT = 0, 1
 HOST, DEVICE = 0, 1
 
 OK, ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_NOMEM = 0, 1, 2, 3, 4
-KERNEL_EUROPEAN, KERNEL_BULLET, KERNEL_TRAJECTORY, KERNEL_NESTED = 0, 1, 2, 3
+KERNEL_EUROPEAN, KERNEL_BULLET, KERNEL_TRAJECTORY, KERNEL_NESTED, KERNEL_SWEEP = 0, 1, 2, 3, 4
 
 
 class McbError(RuntimeError):

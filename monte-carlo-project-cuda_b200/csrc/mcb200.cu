@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -88,6 +89,8 @@ struct mcb_engine {
     DeviceBuffer<ResultDev> results;
     DeviceBuffer<unsigned char> scratch;   // hooks / host<->device staging
     DeviceBuffer<float> nested_ws;         // nested MC: log2 S, (prices), (counts) of the outer points
+    DeviceBuffer<float4> sweep_sets;       // sweep: (c0, c1, K, -) per parameter set
+    std::vector<float4> h_sweep_sets;      // host staging for sweep_sets (pageable on purpose)
     mcb_result *h_results = nullptr;       // pinned
     size_t h_results_cap = 0;
     double *h_segments = nullptr;          // pinned, [MCB_SEGMENTS][2] of the last whole-job call
@@ -344,6 +347,7 @@ int mcb_engine_destroy(mcb_engine *e)
     e->results.release();
     e->scratch.release();
     e->nested_ws.release();
+    e->sweep_sets.release();
     if (e->h_results) cudaFreeHost(e->h_results);
     if (e->h_segments) cudaFreeHost(e->h_segments);
     delete e;
@@ -564,20 +568,45 @@ int mcb_sweep_segments_async(mcb_engine *e, const mcb_option_data *opt, const fl
     uint64_t c_lo, c_hi;
     segment_span(rank, world, n_chunks, &seg_lo, &seg_hi, &c_lo, &c_hi);
     const uint64_t local = c_hi - c_lo;
-    // Parameter sets are priced in groups so the partials workspace stays bounded (<= 64 MiB).
-    uint64_t group = local ? (uint64_t)(8u << 20) / (local ? local : 1) : (uint64_t)n_params;
+    if (local > 0x7fffffffull) return fail(MCB_ERR_INVALID, "too many chunks for one launch");
+    // Parameter sets are priced in groups so the partials workspace stays bounded (<= 64 MiB);
+    // within a group ONE launch draws every path once and walks all the sets (sweep_kernel).
+    uint64_t group = local ? (uint64_t)(8u << 20) / local : (uint64_t)n_params;
     if (group < 1) group = 1;
     if (group > (uint64_t)n_params) group = (uint64_t)n_params;
-    if ((rc = e->partials.reserve((size_t)(group * (local + 1))))) return rc;
+    const uint64_t stride = local + 1;
+    if ((rc = e->partials.reserve((size_t)(group * stride)))) return rc;
+    // per-set constants (c0, c1, K) folded in double exactly as european_params does
+    if ((rc = e->sweep_sets.reserve((size_t)n_params))) return rc;
+    // staged from pageable memory: cudaMemcpyAsync returns once the source has been read, so the
+    // vector can be refilled by the next call without any event bookkeeping
+    e->h_sweep_sets.resize((size_t)n_params);
+    for (int i = 0; i < n_params; ++i) {
+        const EuropeanParams one = european_params(opt, strikes[i], vols[i], n_paths, seed, c_lo);
+        e->h_sweep_sets[i] = make_float4(one.c0, one.c1, one.K, 0.0f);
+    }
+    CU(cudaMemcpyAsync(e->sweep_sets.ptr, e->h_sweep_sets.data(), sizeof(float4) * (size_t)n_params,
+                       cudaMemcpyHostToDevice, st));
+    SweepParams prm{};
+    prm.n_paths = n_paths;
+    prm.first_chunk = c_lo;
+    prm.stride = stride;
+    prm.keys = make_philox_keys(seed);
     for (uint64_t i0 = 0; i0 < (uint64_t)n_params; i0 += group) {
         const uint64_t cnt = (uint64_t)n_params - i0 < group ? (uint64_t)n_params - i0 : group;
-        for (uint64_t j = 0; j < cnt; ++j) {
-            const EuropeanParams prm = european_params(opt, strikes[i0 + j], vols[i0 + j], n_paths, seed, c_lo);
-            if ((rc = launch_european<MCB_EUROPEAN_PATHS_PER_SLOT>(e, prm, option_type, local,
-                                                                   e->partials.ptr + j * (local + 1), nullptr, 0, st)))
-                return rc;
+        prm.n_sets = (int)cnt;
+        if (local) {
+            TimedScope timed(e, MCB_KERNEL_SWEEP, st);
+            if (option_type == MCB_PUT)
+                sweep_kernel<kPut, MCB_EUROPEAN_PATHS_PER_SLOT><<<(unsigned)local, kSlots, 0, st>>>(
+                    prm, e->sweep_sets.ptr + i0, e->partials.ptr);
+            else
+                sweep_kernel<kCall, MCB_EUROPEAN_PATHS_PER_SLOT><<<(unsigned)local, kSlots, 0, st>>>(
+                    prm, e->sweep_sets.ptr + i0, e->partials.ptr);
+            e->launches++;
+            CU(cudaGetLastError());
         }
-        if ((rc = launch_segments(e, e->partials.ptr, local + 1, c_lo, n_chunks, seg_lo, seg_hi, (int)cnt,
+        if ((rc = launch_segments(e, e->partials.ptr, stride, c_lo, n_chunks, seg_lo, seg_hi, (int)cnt,
                                   d_segments + i0 * 2 * MCB_SEGMENTS, st)))
             return rc;
     }
@@ -617,27 +646,36 @@ static int trajectories_launch(mcb_engine *e, const mcb_option_data *opt, uint64
     prm.first_path = first_path;
     prm.n_paths = n_paths;
     prm.keys = make_philox_keys(seed);
-    const uint64_t rows_per_cta = (uint64_t)kPathWarps * kPathsPerWarp;
+    // row layout: 0 = 32 lanes x 4 steps, 1 = 32 lanes x 8 steps, 2 = 16 lanes x 16 steps (two rows per warp)
+    int layout = opt->N_STEPS > 128 ? 1 : 0;
+    if (const char *env = getenv("MCB_TRAJ_LAYOUT")) layout = atoi(env);  // tuning knob, results identical per layout? no: see DESIGN
+    const bool wide = layout == 2;
+    const uint64_t rows_per_cta = (uint64_t)kPathWarps * kPathsPerWarp * (wide ? 2 : 1);
     const uint64_t ctas = (n_paths + rows_per_cta - 1) / rows_per_cta;
-    if (ctas > 0x7fffffffull) return fail(MCB_ERR_INVALID, "too many paths for one launch");
+    if (ctas > 0x7fffffffull || n_paths > 0x7fffffffull) return fail(MCB_ERR_INVALID, "too many paths for one launch");
     const bool vec = (opt->N_STEPS % 4 == 0) && ((uintptr_t)d_prices % 16 == 0) &&
                      (!d_counts || (uintptr_t)d_counts % 16 == 0) && (!d_logs || (uintptr_t)d_logs % 16 == 0);
-    const bool wide = opt->N_STEPS > 128;  // 8 steps per lane (two Philox blocks) for long rows
     cudaStream_t st = pick(e, stream);
     {
         TimedScope timed(e, MCB_KERNEL_TRAJECTORY, st);
         const unsigned g = (unsigned)ctas, b = kPathWarps * 32;
-#define MCB_TRAJ(SPL, VEC, CNT) trajectory_kernel<SPL, VEC, CNT><<<g, b, 0, st>>>(prm, d_prices, d_counts, d_logs)
-        if (wide) {
-            if (vec && d_counts) MCB_TRAJ(8, true, true);
-            else if (vec) MCB_TRAJ(8, true, false);
-            else if (d_counts) MCB_TRAJ(8, false, true);
-            else MCB_TRAJ(8, false, false);
+#define MCB_TRAJ(SPL, LPR, VEC, CNT) \
+    trajectory_kernel<SPL, LPR, VEC, CNT><<<g, b, 0, st>>>(prm, d_prices, d_counts, d_logs)
+        if (layout == 2) {
+            if (vec && d_counts) MCB_TRAJ(16, 16, true, true);
+            else if (vec) MCB_TRAJ(16, 16, true, false);
+            else if (d_counts) MCB_TRAJ(16, 16, false, true);
+            else MCB_TRAJ(16, 16, false, false);
+        } else if (layout == 1) {
+            if (vec && d_counts) MCB_TRAJ(8, 32, true, true);
+            else if (vec) MCB_TRAJ(8, 32, true, false);
+            else if (d_counts) MCB_TRAJ(8, 32, false, true);
+            else MCB_TRAJ(8, 32, false, false);
         } else {
-            if (vec && d_counts) MCB_TRAJ(4, true, true);
-            else if (vec) MCB_TRAJ(4, true, false);
-            else if (d_counts) MCB_TRAJ(4, false, true);
-            else MCB_TRAJ(4, false, false);
+            if (vec && d_counts) MCB_TRAJ(4, 32, true, true);
+            else if (vec) MCB_TRAJ(4, 32, true, false);
+            else if (d_counts) MCB_TRAJ(4, 32, false, true);
+            else MCB_TRAJ(4, 32, false, false);
         }
 #undef MCB_TRAJ
     }

@@ -19,13 +19,14 @@ namespace mcb {
 // The reference stores one float per thread per step with a warp stride of n_steps*4 bytes
 // (inc/trajectories.cuh:304-305): every store touches its own 32-byte sector.
 //
-// Here the STEPS of a path are spread over the lanes of a warp, which the stateless generator
-// allows (normal i of path p is a pure function of (seed, p, i)): lane j draws the SPL (4 or 8)
-// consecutive normals of steps [SPL*j, SPL*j + SPL) from its own Philox block(s), forms the
-// in-lane prefix of the log2 increments, a 5-stage shuffle scan over the lane totals supplies
-// each lane's starting log-price, and the warp then stores 32*SPL consecutive floats of ONE row:
-// fully coalesced STG.128 with no shared-memory staging, no transposition and no barrier.
-// Rows longer than 32*SPL steps take several passes with the running log-price carried in a
+// Here the STEPS of a path are spread over LPR lanes of a warp (32, or 16 with two rows side by
+// side), which the stateless generator allows (normal i of path p is a pure function of
+// (seed, p, i)): lane j draws the SPL consecutive normals of steps [SPL*j, SPL*j + SPL) from its
+// own Philox block(s), forms the in-lane prefix of the log2 increments, a log2(LPR)-stage
+// shuffle scan over the lane totals supplies each lane's starting log-price, and the lanes then
+// store LPR*SPL consecutive floats of ONE row: every lane writes SPL*4 contiguous bytes
+// (whole 32-byte sectors) with STG.128, no shared-memory staging, no transposition, no barrier.
+// Rows longer than LPR*SPL steps take several passes with the running log-price carried in a
 // register.  The summation order is a function of the step index only, so a row does not depend
 // on which launch, slab or GPU produced it.
 // ------------------------------------------------------------------------------------------
@@ -41,73 +42,83 @@ struct PathParams {
 constexpr int kPathWarps = 8;     // warps (= rows in flight) per CTA
 constexpr int kPathsPerWarp = 8;  // rows a warp walks one after the other
 
-// One stage of an inclusive warp scan: x += (value of lane - off), when that lane exists.
-// shfl.sync.up hands back the "source lane in range" predicate, so a stage is SHFL + one
-// predicated add (the C++ intrinsic costs SHFL + FADD + FSEL).
+// One stage of an inclusive scan over groups of LPR lanes: x += (value of lane - off) when
+// that lane is in the same group.  shfl.sync.up hands back the "source lane in range" predicate,
+// so a stage is SHFL + one predicated add (the C++ intrinsic costs SHFL + FADD + FSEL).
+template <int LPR>
 __device__ __forceinline__ float scan_stage(float x, int off)
 {
     asm("{ .reg .f32 t; .reg .pred p;\n\t"
-        "shfl.sync.up.b32 t|p, %0, %1, 0, 0xffffffff;\n\t"
+        "shfl.sync.up.b32 t|p, %0, %1, %2, 0xffffffff;\n\t"
         "@p add.f32 %0, %0, t; }"
-        : "+f"(x) : "r"(off));
+        : "+f"(x) : "r"(off), "n"((32 - LPR) << 8));
     return x;
 }
+template <int LPR>
 __device__ __forceinline__ int scan_stage(int x, int off)
 {
     asm("{ .reg .b32 t; .reg .pred p;\n\t"
-        "shfl.sync.up.b32 t|p, %0, %1, 0, 0xffffffff;\n\t"
+        "shfl.sync.up.b32 t|p, %0, %1, %2, 0xffffffff;\n\t"
         "@p add.s32 %0, %0, t; }"
-        : "+r"(x) : "r"(off));
+        : "+r"(x) : "r"(off), "n"((32 - LPR) << 8));
     return x;
 }
-// value of the lane below (0 for lane 0)
+// value of the lane below (0 for the first lane of a group)
+template <int LPR>
 __device__ __forceinline__ float shift_up_one(float x)
 {
     float r;
     asm("{ .reg .pred p;\n\t"
-        "shfl.sync.up.b32 %0|p, %1, 1, 0, 0xffffffff;\n\t"
+        "shfl.sync.up.b32 %0|p, %1, 1, %2, 0xffffffff;\n\t"
         "@!p mov.f32 %0, 0f00000000; }"
-        : "=f"(r) : "f"(x));
+        : "=f"(r) : "f"(x), "n"((32 - LPR) << 8));
     return r;
 }
+template <int LPR>
 __device__ __forceinline__ int shift_up_one(int x)
 {
     int r;
     asm("{ .reg .pred p;\n\t"
-        "shfl.sync.up.b32 %0|p, %1, 1, 0, 0xffffffff;\n\t"
+        "shfl.sync.up.b32 %0|p, %1, 1, %2, 0xffffffff;\n\t"
         "@!p mov.b32 %0, 0; }"
-        : "=r"(r) : "r"(x));
+        : "=r"(r) : "r"(x), "n"((32 - LPR) << 8));
     return r;
 }
-// exclusive prefix over the lanes of a warp (lane 0 gets 0): 6 SHFL + 5 adds
-template <typename T>
-__device__ __forceinline__ T warp_exclusive_scan(T x)
+// exclusive prefix over each group of LPR lanes (first lane gets 0): 1 + log2(LPR) SHFL
+template <int LPR, typename T>
+__device__ __forceinline__ T group_exclusive_scan(T x)
 {
-    x = shift_up_one(x);
+    x = shift_up_one<LPR>(x);
 #pragma unroll
-    for (int off = 1; off < 32; off <<= 1) x = scan_stage(x, off);
+    for (int off = 1; off < LPR; off <<= 1) x = scan_stage<LPR>(x, off);
     return x;
 }
 
-// SPL = steps per lane (4: one Philox block, 8: two).  VEC4: rows are 16-byte aligned
+// SPL = steps per lane (a multiple of 4: one Philox block per 4 steps), LPR = lanes per row
+// (32 or 16: a warp walks 32/LPR rows side by side).  VEC4: rows are 16-byte aligned
 // (n_steps % 4 == 0 and aligned base pointers).  logs (nullable): log2 of every stored price,
 // the exact FP32 state nested_kernel restarts its inner paths from.
-template <int SPL, bool VEC4, bool COUNTS>
+template <int SPL, int LPR, bool VEC4, bool COUNTS>
 __global__ void __launch_bounds__(kPathWarps * 32)
 trajectory_kernel(const __grid_constant__ PathParams prm, float *__restrict__ prices, int *__restrict__ counts,
                   float *__restrict__ logs)
 {
     constexpr int kBlocks = SPL / 4;
+    constexpr int kRowsPerWarp = 32 / LPR;             // rows walked side by side
+    constexpr int kPassSteps = SPL * LPR;              // steps of a row covered per pass
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sub = lane / LPR, ln = lane % LPR;       // which of the side-by-side rows, lane within it
     const int n_steps = prm.n_steps;
     // launch-local row indices fit 32 bits (the host caps a launch at 2^31 rows)
     const uint32_t n_rows = (uint32_t)prm.n_paths;
-    uint32_t row = (blockIdx.x * kPathWarps + warp) * kPathsPerWarp;
-    const uint32_t row_end = min(row + (uint32_t)kPathsPerWarp, n_rows);
-    const int lane_step = SPL * lane;
+    const uint32_t row_first = (blockIdx.x * kPathWarps + warp) * (kPathsPerWarp * kRowsPerWarp);
+    const int lane_step = SPL * ln;
 
 #pragma unroll 1
-    for (; row < row_end; ++row) {
+    for (int r = 0; r < kPathsPerWarp; ++r) {
+        if (row_first + (uint32_t)(r * kRowsPerWarp) >= n_rows) break;   // warp-uniform
+        const uint32_t row = row_first + (uint32_t)(r * kRowsPerWarp + sub);
+        const bool row_ok = row < n_rows;               // a ragged last group computes and discards
         const uint64_t p = prm.first_path + row;
         const uint32_t p_lo = (uint32_t)p, p_hi = (uint32_t)(p >> 32);
         const uint64_t row_off = (uint64_t)row * (uint32_t)n_steps + (uint32_t)lane_step;
@@ -118,7 +129,7 @@ trajectory_kernel(const __grid_constant__ PathParams prm, float *__restrict__ pr
         int carry_c = 0;
 
 #pragma unroll 1
-        for (int step0 = 0; step0 < n_steps; step0 += 32 * SPL) {
+        for (int step0 = 0; step0 < n_steps; step0 += kPassSteps) {
             const int my_step = step0 + lane_step;
             const bool active = my_step < n_steps;
             // Branch-free on purpose: lanes past the end of the row (only ever the tail lanes of
@@ -131,50 +142,48 @@ trajectory_kernel(const __grid_constant__ PathParams prm, float *__restrict__ pr
 #pragma unroll
             for (int j = 1; j < SPL; ++j) a[j] = a[j] + a[j - 1];
             const float lane_total = active ? a[SPL - 1] : 0.0f;
-            const float base = carry_l + warp_exclusive_scan(lane_total);
-            float s[SPL];
-            int c[SPL];
-#pragma unroll
-            for (int j = 0; j < SPL; ++j) {
-                a[j] = base + a[j];
-                s[j] = mufu_ex2(a[j]);
-            }
-            carry_l = __shfl_sync(kFullMask, base + lane_total, 31);
+            const float base = carry_l + group_exclusive_scan<LPR>(lane_total);
+            carry_l = __shfl_sync(kFullMask, base + lane_total, LPR - 1, LPR);
+
+            int cbase = 0;
             if (COUNTS) {
                 int run = 0;
 #pragma unroll
-                for (int j = 0; j < SPL; ++j) {
-                    run += (a[j] < prm.lB && my_step + j < n_steps) ? 1 : 0;
-                    c[j] = run;
-                }
-                const int cbase = carry_c + warp_exclusive_scan(run);
-#pragma unroll
-                for (int j = 0; j < SPL; ++j) c[j] += cbase;
-                carry_c = __shfl_sync(kFullMask, c[SPL - 1], 31);
+                for (int j = 0; j < SPL; ++j) run += (base + a[j] < prm.lB && my_step + j < n_steps) ? 1 : 0;
+                cbase = carry_c + group_exclusive_scan<LPR>(run);
+                carry_c = __shfl_sync(kFullMask, cbase + run, LPR - 1, LPR);
             }
 
-            if (active) {
-                if (VEC4) {  // n_steps % 4 == 0: whole float4s are in range
+            if (active && row_ok) {
 #pragma unroll
-                    for (int b = 0; b < kBlocks; ++b) {
-                        if (b == 0 || my_step + 4 * b < n_steps) {
-                            __stcs(reinterpret_cast<float4 *>(out_p + step0) + b,
-                                   make_float4(s[4 * b], s[4 * b + 1], s[4 * b + 2], s[4 * b + 3]));
-                            if (COUNTS)
-                                __stcs(reinterpret_cast<int4 *>(out_c + step0) + b,
-                                       make_int4(c[4 * b], c[4 * b + 1], c[4 * b + 2], c[4 * b + 3]));
-                            if (logs)
-                                __stcs(reinterpret_cast<float4 *>(out_l + step0) + b,
-                                       make_float4(a[4 * b], a[4 * b + 1], a[4 * b + 2], a[4 * b + 3]));
+                for (int b = 0; b < kBlocks; ++b) {
+                    float l[4], s[4];
+                    int c[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        l[j] = base + a[4 * b + j];
+                        s[j] = mufu_ex2(l[j]);
+                        if (COUNTS) {
+                            cbase += (l[j] < prm.lB) ? 1 : 0;
+                            c[j] = cbase;
                         }
                     }
-                } else {
+                    if (VEC4) {  // n_steps % 4 == 0: whole float4s are in range
+                        if (b == 0 || my_step + 4 * b < n_steps) {
+                            __stcs(reinterpret_cast<float4 *>(out_p + step0) + b, make_float4(s[0], s[1], s[2], s[3]));
+                            if (COUNTS)
+                                __stcs(reinterpret_cast<int4 *>(out_c + step0) + b, make_int4(c[0], c[1], c[2], c[3]));
+                            if (logs)
+                                __stcs(reinterpret_cast<float4 *>(out_l + step0) + b, make_float4(l[0], l[1], l[2], l[3]));
+                        }
+                    } else {
 #pragma unroll
-                    for (int j = 0; j < SPL; ++j) {
-                        if (my_step + j < n_steps) {
-                            __stcs(out_p + step0 + j, s[j]);
-                            if (COUNTS) __stcs(out_c + step0 + j, c[j]);
-                            if (logs) __stcs(out_l + step0 + j, a[j]);
+                        for (int j = 0; j < 4; ++j) {
+                            if (my_step + 4 * b + j < n_steps) {
+                                __stcs(out_p + step0 + 4 * b + j, s[j]);
+                                if (COUNTS) __stcs(out_c + step0 + 4 * b + j, c[j]);
+                                if (logs) __stcs(out_l + step0 + 4 * b + j, l[j]);
+                            }
                         }
                     }
                 }

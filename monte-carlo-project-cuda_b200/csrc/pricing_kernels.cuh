@@ -80,6 +80,113 @@ european_kernel(const __grid_constant__ EuropeanParams prm, float2 *__restrict__
 }
 
 // ------------------------------------------------------------------------------------------
+// Batched strike/vol sweep with common random numbers (BASELINE config 5): every parameter set
+// is priced on the SAME draws, so the Philox + Box-Muller work is done once per path and only
+//   FFMA, MUFU.EX2, FADD, FMNMX, FADD, FFMA
+// is repeated per (path, parameter set) -- the kernel is MUFU-bound (one EX2 per unit).
+// One CTA = one chunk; a thread keeps the 64 unit normals of its slot in registers and walks
+// the parameter sets, folding each set's (sum, sumsq) through the same slot order and the same
+// block tree as european_kernel: partials[set][chunk] is BIT-identical to a separate
+// european_kernel launch with that set's (K, sigma).
+// ------------------------------------------------------------------------------------------
+struct SweepParams {
+    uint64_t n_paths;      // total paths of the run
+    uint64_t first_chunk;  // chunk index of blockIdx.x == 0
+    uint64_t stride;       // float2 elements between consecutive parameter sets in `partials`
+    int n_sets;
+    uint32_t pad;
+    PhiloxKeys keys;
+};
+
+constexpr int kSweepTile = 4;  // parameter sets folded together (8 values through one tree)
+
+template <int TYPE, int PPS>
+__global__ void __launch_bounds__(kSlots)
+sweep_kernel(const __grid_constant__ SweepParams prm, const float4 *__restrict__ sets /* (c0, c1, K, -) */,
+             float2 *__restrict__ partials)
+{
+    __shared__ float scratch[2 * kSweepTile][kWarps];
+    const uint64_t chunk = prm.first_chunk + blockIdx.x;
+    const uint64_t base = chunk * (uint64_t)(kSlots * PPS);
+    const uint32_t p_hi = (uint32_t)(base >> 32);
+    const uint32_t p_lo0 = (uint32_t)base + threadIdx.x;
+    const uint64_t left = prm.n_paths - base;
+    // paths of this slot that exist: chunk-local indices t, t+256, ... < left
+    const int n_valid = left >= (uint64_t)(kSlots * PPS)
+                            ? PPS
+                            : (int)((left + (uint64_t)(kSlots - 1) - threadIdx.x) / kSlots);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    float unit[PPS];  // normal / sqrt(2 ln 2) of every path of the slot
+#pragma unroll
+    for (int i = 0; i < PPS; ++i) {
+        const Words4 w = philox4x32_10(0u, 0u, p_lo0 + (uint32_t)(i * kSlots), p_hi, prm.keys);
+        unit[i] = unit_normal_sin(w.x, w.y);
+    }
+
+    for (int s0 = 0; s0 < prm.n_sets; s0 += kSweepTile) {
+        float sum[kSweepTile], sq[kSweepTile];
+#pragma unroll
+        for (int k = 0; k < kSweepTile; ++k) {
+            sum[k] = 0.0f;
+            sq[k] = 0.0f;
+            if (s0 + k < prm.n_sets) {
+                const float4 c = __ldg(sets + s0 + k);
+                if (n_valid == PPS) {
+#pragma unroll
+                    for (int i = 0; i < PPS; ++i) {
+                        const float St = mufu_ex2(fmaf(c.y, unit[i], c.x));
+                        const float pay = TYPE == kPut ? fmaxf(c.z - St, 0.0f) : fmaxf(St - c.z, 0.0f);
+                        sum[k] = sum[k] + pay;
+                        sq[k] = fmaf(pay, pay, sq[k]);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < PPS; ++i) {
+                        if (i < n_valid) {
+                            const float St = mufu_ex2(fmaf(c.y, unit[i], c.x));
+                            const float pay = TYPE == kPut ? fmaxf(c.z - St, 0.0f) : fmaxf(St - c.z, 0.0f);
+                            sum[k] = sum[k] + pay;
+                            sq[k] = fmaf(pay, pay, sq[k]);
+                        }
+                    }
+                }
+            }
+        }
+        // same tree as block_fold2, kSweepTile parameter sets at a time
+#pragma unroll
+        for (int k = 0; k < kSweepTile; ++k) {
+            sum[k] = warp_fold(sum[k]);
+            sq[k] = warp_fold(sq[k]);
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < kSweepTile; ++k) {
+                scratch[2 * k][warp] = sum[k];
+                scratch[2 * k + 1][warp] = sq[k];
+            }
+        }
+        __syncthreads();
+        if (warp == 0) {
+#pragma unroll
+            for (int k = 0; k < 2 * kSweepTile; ++k) {
+                float x = lane < kWarps ? scratch[k][lane] : 0.0f;
+#pragma unroll
+                for (int off = kWarps / 2; off > 0; off >>= 1) x = x + __shfl_down_sync(kFullMask, x, off);
+                if (k & 1) sq[k >> 1] = x; else sum[k >> 1] = x;
+            }
+            if (lane == 0) {
+#pragma unroll
+                for (int k = 0; k < kSweepTile; ++k)
+                    if (s0 + k < prm.n_sets)
+                        partials[(uint64_t)(s0 + k) * prm.stride + blockIdx.x] = make_float2(sum[k], sq[k]);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Multi-step GBM walk in log2 space, fused drift + diffusion: the FFMA that scales the
 // Box-Muller radius by the trig value anyway also applies the volatility and adds the drift
 // (increments4), so a step is ONE FADD, l += d; the barrier test is l < log2 B; one MUFU.EX2 at

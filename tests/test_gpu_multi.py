@@ -1,0 +1,73 @@
+"""Multi-GPU (NCCL) checks of the sharded path: needs >= 2 B200s (`gpurun --gpus 2`); on a 1-GPU
+box the tests skip and tests/test_dist_gloo.py + test_sharded_segments_bit_identical_for_any_world
+cover the same logic."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    import importlib
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as entry
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        pkg = entry.load_package()
+        sharded = importlib.import_module(entry.PKG_NAME + ".sharded")
+        eng = pkg.Engine(rank)
+        pricer = sharded.ShardedPricer(eng)
+        n = 37 * pkg.EUROPEAN_CHUNK + 999
+        opt = pkg.option(N_PATHS=n)
+        res = pricer.price_european(opt, n, 1234, pkg.CALL)
+        put = pricer.price_european(opt, n, 1234, pkg.PUT)
+        ob = pkg.option(N_STEPS=50, N_PATHS=20000, B=120.0, P1=5, P2=40)
+        bul = pricer.price_bullet(ob, 20000, 1234)
+        k = np.linspace(80, 120, 5, dtype=np.float32)
+        v = np.linspace(0.1, 0.5, 5, dtype=np.float32)
+        sw = pricer.price_sweep(opt, k, v, n, 1234, pkg.CALL)
+        # trajectory slabs: no collective, each rank its own contiguous rows
+        lo, hi = pkg.path_span(rank, world, 1000)
+        rows = eng.simulate_trajectories(pkg.option(N_STEPS=64, N_PATHS=1000), lo, hi - lo, 1234)
+        np.save(os.path.join(out_dir, f"r{rank}.npy"),
+                np.array([res.sum, res.sumsq, res.price, put.sum, bul.sum, bul.sumsq] + [x.sum for x in sw]))
+        np.save(os.path.join(out_dir, f"rows{rank}.npy"), rows)
+        eng.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_nccl_sharded_prices_match_single_gpu_bits(tmp_path, pkg, engine):
+    import torch
+    import torch.multiprocessing as mp
+    world = min(torch.cuda.device_count(), 8)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    port = 29600 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    n = 37 * pkg.EUROPEAN_CHUNK + 999
+    opt = pkg.option(N_PATHS=n)
+    res = engine.price_european(opt, n, 1234, pkg.CALL)
+    put = engine.price_european(opt, n, 1234, pkg.PUT)
+    ob = pkg.option(N_STEPS=50, N_PATHS=20000, B=120.0, P1=5, P2=40)
+    bul = engine.price_bullet(ob, 20000, 1234)
+    k = np.linspace(80, 120, 5, dtype=np.float32)
+    v = np.linspace(0.1, 0.5, 5, dtype=np.float32)
+    sw = engine.price_sweep(opt, k, v, n, 1234, pkg.CALL)
+    want = np.array([res.sum, res.sumsq, res.price, put.sum, bul.sum, bul.sumsq] + [x.sum for x in sw])
+    rows = engine.simulate_trajectories(pkg.option(N_STEPS=64, N_PATHS=1000), 0, 1000, 1234)
+    got_rows = []
+    for r in range(world):
+        got = np.load(tmp_path / f"r{r}.npy")
+        assert (got == want).all(), (r, got, want)          # bit-identical on every rank
+        got_rows.append(np.load(tmp_path / f"rows{r}.npy"))
+    assert (np.concatenate(got_rows).view(np.uint32) == rows.view(np.uint32)).all()
