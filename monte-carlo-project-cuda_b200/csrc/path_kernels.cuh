@@ -228,8 +228,23 @@ nested_kernel(const __grid_constant__ NestedParams prm, const float *__restrict_
         float sum = 0.0f, sq = 0.0f;
         if (co <= prm.P2) {
             const uint64_t q = (p * (uint64_t)n_steps + (uint64_t)k) * (uint64_t)prm.n_inner;
+            int jj = threadIdx.x;
 #pragma unroll 1
-            for (int jj = threadIdx.x; jj < prm.n_inner; jj += kSlots) {
+            for (; jj + kSlots < prm.n_inner; jj += 2 * kSlots) {   // two inner paths interleaved
+                const uint64_t sa = q + (uint64_t)jj, sb = sa + kSlots;
+                float l[2] = {lo, lo};
+                int c[2] = {co, co};
+                const uint32_t s_lo[2] = {(uint32_t)sa, (uint32_t)sb};
+                const uint32_t s_hi[2] = {(uint32_t)(sa >> 32), (uint32_t)(sb >> 32)};
+                walk_paths<2>(l, c, s_lo, s_hi, remaining, prm.sc, prm.dr, prm.lB, prm.keys_inner);
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const float pay = (c[k] >= prm.P1 && c[k] <= prm.P2) ? fmaxf(mufu_ex2(l[k]) - prm.K, 0.0f) : 0.0f;
+                    sum = sum + pay;
+                    sq = fmaf(pay, pay, sq);
+                }
+            }
+            if (jj < prm.n_inner) {
                 const uint64_t sub = q + (uint64_t)jj;
                 float l = lo;
                 int c = co;

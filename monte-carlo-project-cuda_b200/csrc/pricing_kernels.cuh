@@ -32,12 +32,33 @@ struct EuropeanParams {
     PhiloxKeys keys;
 };
 
+// Philox block 0 of path p with the first round peeled: the counter is (0, 0, p_lo, p_hi), so
+// round 1 needs only prod1 = M1 * p_lo -- and consecutive paths of a slot differ by 256, so the
+// caller advances prod1 with a 64-bit add (ALU pipe) instead of re-multiplying (fmaheavy pipe,
+// the kernel's bottleneck).  Same words as philox4x32_10(0, 0, p_lo, p_hi).
+__device__ __forceinline__ Words4 philox_block0_from_prod(uint64_t prod1, uint32_t p_hi, const PhiloxKeys &k)
+{
+    uint32_t c0 = (uint32_t)(prod1 >> 32) ^ k.k0[0];
+    uint32_t c1 = (uint32_t)prod1;
+    uint32_t c2 = p_hi ^ k.k1[0];
+    uint32_t c3 = 0u;
+#pragma unroll
+    for (int r = 1; r < 10; ++r) philox_round(c0, c1, c2, c3, k.k0[r], k.k1[r]);
+    return Words4{c0, c1, c2, c3};
+}
+
+template <int TYPE>
+__device__ __forceinline__ float european_payoff_from_prod(uint64_t prod1, uint32_t p_hi, const EuropeanParams &prm)
+{
+    const Words4 w = philox_block0_from_prod(prod1, p_hi, prm.keys);
+    const float St = mufu_ex2(fmaf(prm.c1, unit_normal_sin(w.x, w.y), prm.c0));
+    return TYPE == kPut ? fmaxf(prm.K - St, 0.0f) : fmaxf(St - prm.K, 0.0f);
+}
+
 template <int TYPE>
 __device__ __forceinline__ float european_payoff(uint32_t p_lo, uint32_t p_hi, const EuropeanParams &prm)
 {
-    const Words4 w = philox4x32_10(0u, 0u, p_lo, p_hi, prm.keys);
-    const float St = mufu_ex2(fmaf(prm.c1, unit_normal_sin(w.x, w.y), prm.c0));
-    return TYPE == kPut ? fmaxf(prm.K - St, 0.0f) : fmaxf(St - prm.K, 0.0f);
+    return european_payoff_from_prod<TYPE>((uint64_t)kPhiloxM1 * p_lo, p_hi, prm);
 }
 
 // One CTA = one chunk of kSlots * PPS consecutive paths.  Slot t (= thread t) accumulates
@@ -58,9 +79,11 @@ european_kernel(const __grid_constant__ EuropeanParams prm, float2 *__restrict__
 
     float sum = 0.0f, sq = 0.0f;
     if (left >= (uint64_t)(kSlots * PPS) && payoffs == nullptr) {
+        uint64_t prod1 = (uint64_t)kPhiloxM1 * p_lo0;   // a chunk never wraps p_lo, so this stays M1 * p_lo
 #pragma unroll 4
         for (int i = 0; i < PPS; ++i) {
-            const float pay = european_payoff<TYPE>(p_lo0 + (uint32_t)(i * kSlots), p_hi, prm);
+            const float pay = european_payoff_from_prod<TYPE>(prod1, p_hi, prm);
+            prod1 += (uint64_t)kPhiloxM1 * kSlots;
             sum = sum + pay;
             sq = fmaf(pay, pay, sq);
         }
@@ -207,33 +230,57 @@ struct WalkParams {
     PhiloxKeys keys;
 };
 
-// Walk `n_steps` steps of stream (keys, subsequence) from (l, count); normal i of the stream
-// drives step i.
-__device__ __forceinline__ void walk_path(float &l, int &count, uint32_t s_lo, uint32_t s_hi, int n_steps,
-                                          float sc, float dr, float lB, const PhiloxKeys &keys)
+// Walk `n_steps` steps of N independent streams (keys, subsequence[k]) from (l[k], count[k]);
+// normal i of a stream drives step i.  N > 1 interleaves the integer (Philox) chains of several
+// paths in one thread: same arithmetic per path, more instruction-level parallelism.
+template <int N>
+__device__ __forceinline__ void walk_paths(float (&l)[N], int (&count)[N], const uint32_t (&s_lo)[N],
+                                           const uint32_t (&s_hi)[N], int n_steps, float sc, float dr, float lB,
+                                           const PhiloxKeys &keys)
 {
     const int full = n_steps >> 2;
+#pragma unroll 1
     for (int b = 0; b < full; ++b) {
-        float d[4];
-        increments4(philox4x32_10((uint32_t)b, 0u, s_lo, s_hi, keys), sc, dr, d);
+        float d[N][4];
+#pragma unroll
+        for (int k = 0; k < N; ++k) increments4(philox4x32_10((uint32_t)b, 0u, s_lo[k], s_hi[k], keys), sc, dr, d[k]);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            l = l + d[j];
-            count += (l < lB) ? 1 : 0;
+#pragma unroll
+            for (int k = 0; k < N; ++k) {
+                l[k] = l[k] + d[k][j];
+                count[k] += (l[k] < lB) ? 1 : 0;
+            }
         }
     }
     const int tail = n_steps & 3;
     if (tail) {
-        float d[4];
-        increments4(philox4x32_10((uint32_t)full, 0u, s_lo, s_hi, keys), sc, dr, d);
+        float d[N][4];
+#pragma unroll
+        for (int k = 0; k < N; ++k)
+            increments4(philox4x32_10((uint32_t)full, 0u, s_lo[k], s_hi[k], keys), sc, dr, d[k]);
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
             if (j < tail) {
-                l = l + d[j];
-                count += (l < lB) ? 1 : 0;
+#pragma unroll
+                for (int k = 0; k < N; ++k) {
+                    l[k] = l[k] + d[k][j];
+                    count[k] += (l[k] < lB) ? 1 : 0;
+                }
             }
         }
     }
+}
+
+__device__ __forceinline__ void walk_path(float &l, int &count, uint32_t s_lo, uint32_t s_hi, int n_steps,
+                                          float sc, float dr, float lB, const PhiloxKeys &keys)
+{
+    float l1[1] = {l};
+    int c1[1] = {count};
+    const uint32_t lo1[1] = {s_lo}, hi1[1] = {s_hi};
+    walk_paths<1>(l1, c1, lo1, hi1, n_steps, sc, dr, lB, keys);
+    l = l1[0];
+    count = c1[0];
 }
 
 __device__ __forceinline__ float bullet_payoff_from(float l, int count, const WalkParams &prm)
@@ -252,10 +299,26 @@ bullet_kernel(const __grid_constant__ WalkParams prm, float2 *__restrict__ parti
     const uint64_t base = chunk * (uint64_t)(kSlots * PPS);
     const uint64_t left = prm.n_paths - base;
     float sum = 0.0f, sq = 0.0f;
+    static_assert(PPS % 2 == 0, "paths of a slot are walked two at a time");
 #pragma unroll 1
-    for (int i = 0; i < PPS; ++i) {
+    for (int i = 0; i < PPS; i += 2) {
         const uint32_t local = (uint32_t)(i * kSlots) + threadIdx.x;
-        if ((uint64_t)local < left) {
+        if ((uint64_t)local + kSlots < left) {
+            // both paths of the pair exist: walk them interleaved, accumulate in slot order
+            const uint64_t pa = base + local, pb = pa + kSlots;
+            float l[2] = {prm.l0, prm.l0};
+            int count[2] = {prm.count0, prm.count0};
+            const uint32_t lo[2] = {(uint32_t)pa, (uint32_t)pb}, hi[2] = {(uint32_t)(pa >> 32), (uint32_t)(pb >> 32)};
+            walk_paths<2>(l, count, lo, hi, prm.n_steps, prm.sc, prm.dr, prm.lB, prm.keys);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const float pay = bullet_payoff_from(l[k], count[k], prm);
+                sum = sum + pay;
+                sq = fmaf(pay, pay, sq);
+                const uint64_t p = k ? pb : pa;
+                if (payoffs && p >= payoffs_first_path) payoffs[p - payoffs_first_path] = pay;
+            }
+        } else if ((uint64_t)local < left) {
             const uint64_t p = base + local;
             float l = prm.l0;
             int count = prm.count0;
