@@ -646,37 +646,46 @@ static int trajectories_launch(mcb_engine *e, const mcb_option_data *opt, uint64
     prm.first_path = first_path;
     prm.n_paths = n_paths;
     prm.keys = make_philox_keys(seed);
-    // row layout: 0 = 32 lanes x 4 steps, 1 = 32 lanes x 8 steps, 2 = 16 lanes x 16 steps (two rows per warp)
-    int layout = opt->N_STEPS > 128 ? 1 : 0;
-    if (const char *env = getenv("MCB_TRAJ_LAYOUT")) layout = atoi(env);  // tuning knob, results identical per layout? no: see DESIGN
-    const bool wide = layout == 2;
-    const uint64_t rows_per_cta = (uint64_t)kPathWarps * kPathsPerWarp * (wide ? 2 : 1);
-    const uint64_t ctas = (n_paths + rows_per_cta - 1) / rows_per_cta;
-    if (ctas > 0x7fffffffull || n_paths > 0x7fffffffull) return fail(MCB_ERR_INVALID, "too many paths for one launch");
+    // Row layout, a function of n_steps ONLY (so a row's bits never depend on which arrays were
+    // asked for): rows of <= 128 steps use 32 lanes x 4 steps, longer rows 32 lanes x 8 steps.
+    const bool wide = opt->N_STEPS > 128;
+    const int pass_steps = wide ? 256 : 128;
+    if (n_paths > 0x7fffffffull) return fail(MCB_ERR_INVALID, "too many paths for one launch");
     const bool vec = (opt->N_STEPS % 4 == 0) && ((uintptr_t)d_prices % 16 == 0) &&
                      (!d_counts || (uintptr_t)d_counts % 16 == 0) && (!d_logs || (uintptr_t)d_logs % 16 == 0);
     cudaStream_t st = pick(e, stream);
-    {
+    // prices only, single-pass rows, aligned: the TMA slab kernel (the bandwidth path, config 3)
+    bool slab = vec && !d_counts && !d_logs && opt->N_STEPS <= pass_steps;
+    if (const char *env = getenv("MCB_TRAJ_SLAB")) slab = slab && atoi(env) != 0;   // tuning knob
+    if (slab) {
+        constexpr int kSlabRows = 4;
+        const uint64_t rows_per_cta = (uint64_t)kPathWarps * kSlabRows;
+        const uint64_t ctas = (n_paths + rows_per_cta - 1) / rows_per_cta;
+        const size_t smem = (size_t)kPathWarps * kSlabRows * (size_t)opt->N_STEPS * sizeof(float);
+        TimedScope timed(e, MCB_KERNEL_TRAJECTORY, st);
+        if (wide)
+            trajectory_slab_kernel<8, 32, kSlabRows><<<(unsigned)ctas, kPathWarps * 32, smem, st>>>(prm, d_prices);
+        else
+            trajectory_slab_kernel<4, 32, kSlabRows><<<(unsigned)ctas, kPathWarps * 32, smem, st>>>(prm, d_prices);
+    } else {
+        const uint64_t rows_per_cta = (uint64_t)kPathWarps * kPathsPerWarp;
+        const uint64_t ctas = (n_paths + rows_per_cta - 1) / rows_per_cta;
         TimedScope timed(e, MCB_KERNEL_TRAJECTORY, st);
         const unsigned g = (unsigned)ctas, b = kPathWarps * 32;
-#define MCB_TRAJ(SPL, LPR, VEC, CNT) \
-    trajectory_kernel<SPL, LPR, VEC, CNT><<<g, b, 0, st>>>(prm, d_prices, d_counts, d_logs)
-        if (layout == 2) {
-            if (vec && d_counts) MCB_TRAJ(16, 16, true, true);
-            else if (vec) MCB_TRAJ(16, 16, true, false);
-            else if (d_counts) MCB_TRAJ(16, 16, false, true);
-            else MCB_TRAJ(16, 16, false, false);
-        } else if (layout == 1) {
-            if (vec && d_counts) MCB_TRAJ(8, 32, true, true);
-            else if (vec) MCB_TRAJ(8, 32, true, false);
-            else if (d_counts) MCB_TRAJ(8, 32, false, true);
-            else MCB_TRAJ(8, 32, false, false);
-        } else {
-            if (vec && d_counts) MCB_TRAJ(4, 32, true, true);
-            else if (vec) MCB_TRAJ(4, 32, true, false);
-            else if (d_counts) MCB_TRAJ(4, 32, false, true);
-            else MCB_TRAJ(4, 32, false, false);
-        }
+#define MCB_TRAJ(SPL, STORE, CNT) trajectory_kernel<SPL, 32, STORE, CNT><<<g, b, 0, st>>>(prm, d_prices, d_counts, d_logs)
+#define MCB_TRAJ_STORES(SPL)                                          \
+    do {                                                              \
+        if (vec) {                                                    \
+            if (d_counts) MCB_TRAJ(SPL, kStoreVec4, true);            \
+            else MCB_TRAJ(SPL, kStoreVec4, false);                    \
+        } else {                                                      \
+            if (d_counts) MCB_TRAJ(SPL, kStoreScalar, true);          \
+            else MCB_TRAJ(SPL, kStoreScalar, false);                  \
+        }                                                             \
+    } while (0)
+        if (wide) MCB_TRAJ_STORES(8);
+        else MCB_TRAJ_STORES(4);
+#undef MCB_TRAJ_STORES
 #undef MCB_TRAJ
     }
     e->launches++;

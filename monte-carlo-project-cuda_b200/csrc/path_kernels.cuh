@@ -94,11 +94,54 @@ __device__ __forceinline__ T group_exclusive_scan(T x)
     return x;
 }
 
+// ---- TMA bulk store helpers (cp.async.bulk shared::cta -> global, bulk_group completion) ----
+__device__ __forceinline__ uint32_t smem_addr(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void bulk_store(void *gmem, const void *smem, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 :: "l"(gmem), "r"(smem_addr(smem)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+enum { kStoreScalar = 0,   // any n_steps / alignment: 4-byte streaming stores
+       kStoreVec4 = 1 };   // rows 16-byte aligned: STG.128 straight from registers
+
+// One pass of one row: lane `ln` of the row's LPR lanes draws the SPL normals of steps
+// [my_step, my_step + SPL), turns them into log2 increments, prefixes them in-lane and across the
+// lanes (scan), and returns the log2 price BEFORE its first step in `base`; a[j] is the in-lane
+// inclusive prefix, so step my_step + j ends at log2 price base + a[j].  carry_l (the log2 price
+// at the start of the pass) is advanced to the end of the pass.  Both trajectory kernels go
+// through this function, so a row's bits do not depend on which of them produced it.
+template <int SPL, int LPR>
+__device__ __forceinline__ float row_pass(const PathParams &prm, uint32_t p_lo, uint32_t p_hi, int my_step,
+                                          bool active, float &carry_l, float (&a)[SPL])
+{
+#pragma unroll
+    for (int b = 0; b < SPL / 4; ++b)
+        increments4(philox4x32_10((uint32_t)(my_step >> 2) + b, 0u, p_lo, p_hi, prm.keys), prm.sc, prm.dr, a + 4 * b);
+#pragma unroll
+    for (int j = 1; j < SPL; ++j) a[j] = a[j] + a[j - 1];
+    // lanes past the end of the row computed garbage (branch-free, the warp stays converged for
+    // the shuffles); they must not leak into the scan
+    const float lane_total = active ? a[SPL - 1] : 0.0f;
+    const float base = carry_l + group_exclusive_scan<LPR>(lane_total);
+    carry_l = __shfl_sync(kFullMask, base + lane_total, LPR - 1, LPR);
+    return base;
+}
+
+// ------------------------------------------------------------------------------------------
+// General kernel: any n_steps (several passes per row), optional barrier counts and log2 prices.
 // SPL = steps per lane (a multiple of 4: one Philox block per 4 steps), LPR = lanes per row
-// (32 or 16: a warp walks 32/LPR rows side by side).  VEC4: rows are 16-byte aligned
-// (n_steps % 4 == 0 and aligned base pointers).  logs (nullable): log2 of every stored price,
-// the exact FP32 state nested_kernel restarts its inner paths from.
-template <int SPL, int LPR, bool VEC4, bool COUNTS>
+// (32 or 16: a warp walks 32/LPR rows side by side).  logs (nullable): log2 of every stored
+// price, the exact FP32 state nested_kernel restarts its inner paths from.
+// ------------------------------------------------------------------------------------------
+template <int SPL, int LPR, int STORE, bool COUNTS>
 __global__ void __launch_bounds__(kPathWarps * 32)
 trajectory_kernel(const __grid_constant__ PathParams prm, float *__restrict__ prices, int *__restrict__ counts,
                   float *__restrict__ logs)
@@ -132,18 +175,8 @@ trajectory_kernel(const __grid_constant__ PathParams prm, float *__restrict__ pr
         for (int step0 = 0; step0 < n_steps; step0 += kPassSteps) {
             const int my_step = step0 + lane_step;
             const bool active = my_step < n_steps;
-            // Branch-free on purpose: lanes past the end of the row (only ever the tail lanes of
-            // the last pass) compute and discard, which keeps the warp converged for the shuffles.
-            float a[SPL];  // log2 increments, then their in-lane inclusive prefix
-#pragma unroll
-            for (int b = 0; b < kBlocks; ++b)
-                increments4(philox4x32_10((uint32_t)(my_step >> 2) + b, 0u, p_lo, p_hi, prm.keys), prm.sc, prm.dr,
-                            a + 4 * b);
-#pragma unroll
-            for (int j = 1; j < SPL; ++j) a[j] = a[j] + a[j - 1];
-            const float lane_total = active ? a[SPL - 1] : 0.0f;
-            const float base = carry_l + group_exclusive_scan<LPR>(lane_total);
-            carry_l = __shfl_sync(kFullMask, base + lane_total, LPR - 1, LPR);
+            float a[SPL];
+            const float base = row_pass<SPL, LPR>(prm, p_lo, p_hi, my_step, active, carry_l, a);
 
             int cbase = 0;
             if (COUNTS) {
@@ -168,7 +201,7 @@ trajectory_kernel(const __grid_constant__ PathParams prm, float *__restrict__ pr
                             c[j] = cbase;
                         }
                     }
-                    if (VEC4) {  // n_steps % 4 == 0: whole float4s are in range
+                    if (STORE == kStoreVec4) {  // n_steps % 4 == 0: whole float4s are in range
                         if (b == 0 || my_step + 4 * b < n_steps) {
                             __stcs(reinterpret_cast<float4 *>(out_p + step0) + b, make_float4(s[0], s[1], s[2], s[3]));
                             if (COUNTS)
@@ -189,6 +222,60 @@ trajectory_kernel(const __grid_constant__ PathParams prm, float *__restrict__ pr
                 }
             }
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Slab kernel (prices only, rows of at most SPL*LPR steps, 16-byte aligned rows): the bandwidth
+// path of BASELINE config 3 (2^20 x 252).
+// A lane's SPL*4 bytes are whole 32-byte sectors only when the row starts on a sector, and with
+// 1008-byte rows every other row does not; measured (tools/store_probe.cu) a warp storing 32 B
+// per lane reaches 2.9-3.9 TB/s, fully coalesced lines 7.3 TB/s.  So the lanes park their floats
+// in shared memory (STS.128), and because a warp walks ROWS CONSECUTIVE rows, which are one
+// contiguous slab of ROWS*n_steps*4 bytes in the path-major output, one elected lane hands the
+// whole slab to the TMA engine as a single cp.async.bulk (shared::cta -> global): full lines on
+// the L1->L2 crossbar, no per-row address arithmetic, one fence per slab.
+// Dynamic shared memory: kPathWarps * ROWS * n_steps floats.
+// ------------------------------------------------------------------------------------------
+template <int SPL, int LPR, int ROWS>
+__global__ void __launch_bounds__(kPathWarps * 32)
+trajectory_slab_kernel(const __grid_constant__ PathParams prm, float *__restrict__ prices)
+{
+    constexpr int kBlocks = SPL / 4;
+    constexpr int kRowsPerWarp = 32 / LPR;
+    static_assert(ROWS % kRowsPerWarp == 0, "a slab is a whole number of passes");
+    extern __shared__ __align__(128) float stage[];    // [warp][ROWS][n_steps]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sub = lane / LPR, ln = lane % LPR;
+    const int n_steps = prm.n_steps;
+    const uint32_t n_rows = (uint32_t)prm.n_paths;
+    const uint32_t slab_row = (blockIdx.x * kPathWarps + warp) * ROWS;
+    if (slab_row >= n_rows) return;                     // warp-uniform
+    const int my_step = SPL * ln;
+    const bool active = my_step < n_steps;
+    float *my_stage = stage + (size_t)warp * ROWS * n_steps;
+
+#pragma unroll 1
+    for (int r = 0; r < ROWS; r += kRowsPerWarp) {
+        const uint64_t p = prm.first_path + slab_row + (uint32_t)(r + sub);   // rows past n_rows: computed, not copied
+        float carry_l = prm.l0;
+        float a[SPL];
+        const float base = row_pass<SPL, LPR>(prm, (uint32_t)p, (uint32_t)(p >> 32), my_step, active, carry_l, a);
+        float *dst = my_stage + (r + sub) * n_steps + my_step;
+#pragma unroll
+        for (int b = 0; b < kBlocks; ++b) {
+            const float4 s = make_float4(mufu_ex2(base + a[4 * b]), mufu_ex2(base + a[4 * b + 1]),
+                                         mufu_ex2(base + a[4 * b + 2]), mufu_ex2(base + a[4 * b + 3]));
+            if (my_step + 4 * b < n_steps) *reinterpret_cast<float4 *>(dst + 4 * b) = s;
+        }
+    }
+    fence_async_smem();   // generic-proxy STS -> visible to the async proxy (TMA)
+    __syncwarp();
+    if (lane == 0) {
+        const uint32_t rows = min((uint32_t)ROWS, n_rows - slab_row);
+        bulk_store(prices + (uint64_t)slab_row * (uint32_t)n_steps, my_stage, rows * (uint32_t)n_steps * 4u);
+        bulk_commit();
+        bulk_wait_read<0>();   // shared memory must outlive the copy's reads
     }
 }
 
