@@ -647,7 +647,8 @@ static int trajectories_launch(mcb_engine *e, const mcb_option_data *opt, uint64
     prm.n_paths = n_paths;
     prm.keys = make_philox_keys(seed);
     // Row layout, a function of n_steps ONLY (so a row's bits never depend on which arrays were
-    // asked for): rows of <= 128 steps use 32 lanes x 4 steps, longer rows 32 lanes x 8 steps.
+    // asked for or which kernel wrote it): rows of <= 128 steps use 32 lanes x 4 steps, longer
+    // rows 16 lanes x 16 steps (two rows side by side per warp).
     const bool wide = opt->N_STEPS > 128;
     const int pass_steps = wide ? 256 : 128;
     if (n_paths > 0x7fffffffull) return fail(MCB_ERR_INVALID, "too many paths for one launch");
@@ -655,36 +656,36 @@ static int trajectories_launch(mcb_engine *e, const mcb_option_data *opt, uint64
                      (!d_counts || (uintptr_t)d_counts % 16 == 0) && (!d_logs || (uintptr_t)d_logs % 16 == 0);
     cudaStream_t st = pick(e, stream);
     // prices only, single-pass rows, aligned: the TMA slab kernel (the bandwidth path, config 3)
-    bool slab = vec && !d_counts && !d_logs && opt->N_STEPS <= pass_steps;
-    if (const char *env = getenv("MCB_TRAJ_SLAB")) slab = slab && atoi(env) != 0;   // tuning knob
+    const bool slab = vec && !d_counts && !d_logs && opt->N_STEPS <= pass_steps;
     if (slab) {
-        constexpr int kSlabRows = 4;
-        const uint64_t rows_per_cta = (uint64_t)kPathWarps * kSlabRows;
+        constexpr int kSlabWarps = 4, kSlabRows = 6;   // tuned on B200 at 2^20 x 252 (profiles/r1_trajectory_tuning.txt)
+        const uint64_t rows_per_cta = (uint64_t)kSlabWarps * kSlabRows;
         const uint64_t ctas = (n_paths + rows_per_cta - 1) / rows_per_cta;
-        const size_t smem = (size_t)kPathWarps * kSlabRows * (size_t)opt->N_STEPS * sizeof(float);
+        const size_t smem = (size_t)kSlabWarps * kSlabRows * (size_t)opt->N_STEPS * sizeof(float);   // <= 24 KB
         TimedScope timed(e, MCB_KERNEL_TRAJECTORY, st);
         if (wide)
-            trajectory_slab_kernel<8, 32, kSlabRows><<<(unsigned)ctas, kPathWarps * 32, smem, st>>>(prm, d_prices);
+            trajectory_slab_kernel<16, 16, kSlabRows, kSlabWarps><<<(unsigned)ctas, kSlabWarps * 32, smem, st>>>(prm, d_prices);
         else
-            trajectory_slab_kernel<4, 32, kSlabRows><<<(unsigned)ctas, kPathWarps * 32, smem, st>>>(prm, d_prices);
+            trajectory_slab_kernel<4, 32, kSlabRows, kSlabWarps><<<(unsigned)ctas, kSlabWarps * 32, smem, st>>>(prm, d_prices);
     } else {
-        const uint64_t rows_per_cta = (uint64_t)kPathWarps * kPathsPerWarp;
+        const uint64_t rows_per_cta = (uint64_t)kPathWarps * kPathsPerWarp * (wide ? 2 : 1);
         const uint64_t ctas = (n_paths + rows_per_cta - 1) / rows_per_cta;
         TimedScope timed(e, MCB_KERNEL_TRAJECTORY, st);
         const unsigned g = (unsigned)ctas, b = kPathWarps * 32;
-#define MCB_TRAJ(SPL, STORE, CNT) trajectory_kernel<SPL, 32, STORE, CNT><<<g, b, 0, st>>>(prm, d_prices, d_counts, d_logs)
-#define MCB_TRAJ_STORES(SPL)                                          \
+#define MCB_TRAJ(SPL, LPR, STORE, CNT) \
+    trajectory_kernel<SPL, LPR, STORE, CNT><<<g, b, 0, st>>>(prm, d_prices, d_counts, d_logs)
+#define MCB_TRAJ_STORES(SPL, LPR)                                     \
     do {                                                              \
         if (vec) {                                                    \
-            if (d_counts) MCB_TRAJ(SPL, kStoreVec4, true);            \
-            else MCB_TRAJ(SPL, kStoreVec4, false);                    \
+            if (d_counts) MCB_TRAJ(SPL, LPR, kStoreVec4, true);       \
+            else MCB_TRAJ(SPL, LPR, kStoreVec4, false);               \
         } else {                                                      \
-            if (d_counts) MCB_TRAJ(SPL, kStoreScalar, true);          \
-            else MCB_TRAJ(SPL, kStoreScalar, false);                  \
+            if (d_counts) MCB_TRAJ(SPL, LPR, kStoreScalar, true);     \
+            else MCB_TRAJ(SPL, LPR, kStoreScalar, false);             \
         }                                                             \
     } while (0)
-        if (wide) MCB_TRAJ_STORES(8);
-        else MCB_TRAJ_STORES(4);
+        if (wide) MCB_TRAJ_STORES(16, 16);
+        else MCB_TRAJ_STORES(4, 32);
 #undef MCB_TRAJ_STORES
 #undef MCB_TRAJ
     }

@@ -237,8 +237,8 @@ trajectory_kernel(const __grid_constant__ PathParams prm, float *__restrict__ pr
 // the L1->L2 crossbar, no per-row address arithmetic, one fence per slab.
 // Dynamic shared memory: kPathWarps * ROWS * n_steps floats.
 // ------------------------------------------------------------------------------------------
-template <int SPL, int LPR, int ROWS>
-__global__ void __launch_bounds__(kPathWarps * 32)
+template <int SPL, int LPR, int ROWS, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
 trajectory_slab_kernel(const __grid_constant__ PathParams prm, float *__restrict__ prices)
 {
     constexpr int kBlocks = SPL / 4;
@@ -249,34 +249,44 @@ trajectory_slab_kernel(const __grid_constant__ PathParams prm, float *__restrict
     const int sub = lane / LPR, ln = lane % LPR;
     const int n_steps = prm.n_steps;
     const uint32_t n_rows = (uint32_t)prm.n_paths;
-    const uint32_t slab_row = (blockIdx.x * kPathWarps + warp) * ROWS;
-    if (slab_row >= n_rows) return;                     // warp-uniform
+    const uint32_t n_slabs = (n_rows + ROWS - 1) / ROWS;
+    const uint32_t slab_stride = gridDim.x * WARPS;   // a warp strides over the slabs (one each when the grid covers them)
     const int my_step = SPL * ln;
     const bool active = my_step < n_steps;
     float *my_stage = stage + (size_t)warp * ROWS * n_steps;
+    float *dst0 = my_stage + sub * n_steps + my_step;
 
 #pragma unroll 1
-    for (int r = 0; r < ROWS; r += kRowsPerWarp) {
-        const uint64_t p = prm.first_path + slab_row + (uint32_t)(r + sub);   // rows past n_rows: computed, not copied
-        float carry_l = prm.l0;
-        float a[SPL];
-        const float base = row_pass<SPL, LPR>(prm, (uint32_t)p, (uint32_t)(p >> 32), my_step, active, carry_l, a);
-        float *dst = my_stage + (r + sub) * n_steps + my_step;
+    for (uint32_t slab = blockIdx.x * WARPS + warp; slab < n_slabs; slab += slab_stride) {
+        const uint32_t slab_row = slab * ROWS;
+#pragma unroll 1
+        for (int r = 0; r < ROWS; r += kRowsPerWarp) {
+            const uint64_t p = prm.first_path + slab_row + (uint32_t)(r + sub);   // rows past n_rows: computed, not copied
+            float carry_l = prm.l0;
+            float a[SPL];
+            const float base = row_pass<SPL, LPR>(prm, (uint32_t)p, (uint32_t)(p >> 32), my_step, active, carry_l, a);
 #pragma unroll
-        for (int b = 0; b < kBlocks; ++b) {
-            const float4 s = make_float4(mufu_ex2(base + a[4 * b]), mufu_ex2(base + a[4 * b + 1]),
-                                         mufu_ex2(base + a[4 * b + 2]), mufu_ex2(base + a[4 * b + 3]));
-            if (my_step + 4 * b < n_steps) *reinterpret_cast<float4 *>(dst + 4 * b) = s;
+            for (int j = 0; j < SPL; ++j) a[j] = mufu_ex2(base + a[j]);
+            if (r == 0) {
+                // the previous slab's bulk copy had this whole pass to read the buffer: wait is ~free
+                if (lane == 0) bulk_wait_read<0>();
+                __syncwarp();
+            }
+            float *dst = dst0 + r * n_steps;
+#pragma unroll
+            for (int b = 0; b < kBlocks; ++b)
+                if (my_step + 4 * b < n_steps)
+                    *reinterpret_cast<float4 *>(dst + 4 * b) = make_float4(a[4 * b], a[4 * b + 1], a[4 * b + 2], a[4 * b + 3]);
+        }
+        fence_async_smem();   // generic-proxy STS -> visible to the async proxy (TMA)
+        __syncwarp();
+        if (lane == 0) {
+            const uint32_t rows = min((uint32_t)ROWS, n_rows - slab_row);
+            bulk_store(prices + (uint64_t)slab_row * (uint32_t)n_steps, my_stage, rows * (uint32_t)n_steps * 4u);
+            bulk_commit();
         }
     }
-    fence_async_smem();   // generic-proxy STS -> visible to the async proxy (TMA)
-    __syncwarp();
-    if (lane == 0) {
-        const uint32_t rows = min((uint32_t)ROWS, n_rows - slab_row);
-        bulk_store(prices + (uint64_t)slab_row * (uint32_t)n_steps, my_stage, rows * (uint32_t)n_steps * 4u);
-        bulk_commit();
-        bulk_wait_read<0>();   // shared memory must outlive the copy's reads
-    }
+    if (lane == 0) bulk_wait_read<0>();   // shared memory must outlive the last copy's reads
 }
 
 // ------------------------------------------------------------------------------------------
