@@ -58,6 +58,17 @@ def bs_call(S0, K, T, r, v):
     return S0 * phi(d1) - K * math.exp(-r * T) * phi(d2)
 
 
+def ncu_traffic(kernel):
+    """DRAM bytes per launch (read + write) of `kernel` from the committed ncu --set full capture
+    (profiles/r1_ncu_traffic.json, written by tools/ncu_traffic.py); None when not captured."""
+    path = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+    try:
+        with open(path) as f:
+            return json.load(f)[kernel]["traffic"]
+    except Exception:
+        return None
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -321,7 +332,9 @@ def run_b200(args):
         peak = sms * ISSUE_PER_CLK_PER_SM * sm_max_mhz * 1e6 / 1e12
         line["roofline"] = {
             "bound": "issue", "kernel": "european_kernel", "achieved": achieved, "peak": peak, "unit": "Tinstr/s",
-            "frac": achieved / peak, "traffic": None,
+            "frac": achieved / peak, "traffic": ncu_traffic("european_kernel"),
+            "traffic_note": "DRAM bytes per launch from ncu --set full (profiles/r1_ncu_traffic.json); the kernel "
+                            "reads no global memory, algorithmic bytes = 512 KiB of chunk partials (stay in L2)",
             "per_unit": f"{INSTR_PER_EUROPEAN_PATH} thread-instr/path (SURVEY 8(d))",
             "peak_how": f"{sms} SMs x {ISSUE_PER_CLK_PER_SM} thread-instr/clk x {sm_max_mhz:.0f} MHz ({peak_src} sm_max_mhz)",
             "kernel_ms": 1e3 * per_launch_s, "kernel_launches": kern_n,
@@ -392,8 +405,9 @@ def other_workloads(torch, pkg, eng, hbm_gbs, peak_src):
     kms, kn = eng.timing_read(pkg.KERNEL_TRAJECTORY)
     nbytes = BYTES_PER_TRAJECTORY_STEP * TRAJ_PATHS * TRAJ_STEPS
     gbs = nbytes / (kms * 1e-3 / kn) / 1e9
-    roofline_traj = {"bound": "hbm", "kernel": "trajectory_kernel", "achieved": gbs, "peak": hbm_gbs, "unit": "GB/s",
-                     "frac": gbs / hbm_gbs, "frac_of_8TBs_nominal": gbs / 8000.0, "traffic": None,
+    roofline_traj = {"bound": "hbm", "kernel": "trajectory_slab_kernel", "achieved": gbs, "peak": hbm_gbs, "unit": "GB/s",
+                     "frac": gbs / hbm_gbs, "frac_of_8TBs_nominal": gbs / 8000.0,
+                     "traffic": ncu_traffic("trajectory_slab_kernel"), "algorithmic_bytes": nbytes,
                      "peak_how": f"MEASURED_PEAKS.json hbm_gbs ({peak_src})",
                      "per_unit": "4 B stored per path-step", "kernel_ms": kms / kn, "kernel_launches": kn,
                      "l2": "output 1.06 GB per launch, larger than L2"}
