@@ -130,6 +130,26 @@ int mcb_price_sweep(mcb_engine *e, const mcb_option_data *opt, const float *stri
  * by Simulation::test_reduction, inc/testing.cuh:185-235). */
 int mcb_reduce_sum(mcb_engine *e, const float *x, uint64_t n, int where, float *out);
 
+/* Per-block float sums with the reference's reduce3..6 index ranges (inc/reduce.cuh:9-227) as
+ * Simulation::test_reduction drives them (inc/testing.cuh:185-235): block b of n_blocks sums
+ * x[(b + k*n_blocks)*span .. +span) for k = 0 only (strided == 0: reduce3/4/5, span = 2*threads)
+ * or for every k (strided != 0: reduce6's grid-stride loop).  Each block sum goes through the
+ * engine's fixed 256-slot tree (slot t adds its elements of the block's index list in order),
+ * so it is deterministic; out (host array) receives n_blocks floats. */
+int mcb_reduce_blocks(mcb_engine *e, const float *x, uint64_t n, int where, uint32_t n_blocks, uint64_t span,
+                      int strided, float *out);
+
+/* n standard normals: out[i] = normal i of the stream (seed, subsequence 0), i.e. what
+ * curand_normal would return from curand_init(seed, 0, 0, Philox).  Replaces
+ * generate_random_array / init_random_array (cuRAND host API, inc/testing.cuh:17-42). */
+int mcb_generate_normals(mcb_engine *e, uint64_t seed, uint64_t n, float *out, int where);
+
+/* The reference's only on-disk format (testing.cu:37-47): header "time,trajectory,value", then per
+ * trajectory a t = 0 row with x0 followed by ((1+i)*dt, trajectory, prices[p*n_steps + i]).
+ * prices is a HOST array (e.g. from mcb_simulate_trajectories).  Pure host code. */
+int mcb_write_trajectories_csv(const char *path, const float *prices, uint64_t n_trajectories, int n_steps,
+                               float x0, float dt);
+
 /* European-style pricing from pre-generated normals normals[p*n_steps + i]; payoffs[p].
  * Replaces simulateOptionPriceGPU / simulateOptionPriceMultipleBlockGPU
  * (inc/trajectories.cuh:14-52) and the CPU overload (inc/testing.cuh:75-91). */

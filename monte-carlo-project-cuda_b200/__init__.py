@@ -102,6 +102,9 @@ SIGNATURES = {
     "mcb_price_sweep": (C.c_int, [_vp, _OP, _vp, _vp, C.c_int, _u64, _u64, C.c_int, _RP]),
     "mcb_reduce_sum": (C.c_int, [_vp, _vp, _u64, C.c_int, C.POINTER(C.c_float)]),
     "mcb_price_from_normals": (C.c_int, [_vp, _OP, _vp, _u64, C.c_int, _vp, C.c_int]),
+    "mcb_reduce_blocks": (C.c_int, [_vp, _vp, _u64, C.c_int, C.c_uint32, _u64, C.c_int, _vp]),
+    "mcb_generate_normals": (C.c_int, [_vp, _u64, _u64, _vp, C.c_int]),
+    "mcb_write_trajectories_csv": (C.c_int, [C.c_char_p, _vp, _u64, C.c_int, C.c_float, C.c_float]),
     "mcb_european_segments_async": (C.c_int, [_vp, _OP, _u64, _u64, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "mcb_bullet_segments_async": (C.c_int, [_vp, _OP, _u64, _u64, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int,
                                             _vp, _vp]),
@@ -256,6 +259,19 @@ class Engine:
         _check(self._lib.mcb_reduce_sum(self._h, a.ctypes.data if a.size else None, a.size, HOST, C.byref(out)))
         return np.float32(out.value)
 
+    def reduce_blocks(self, x, n_blocks, span, strided=False):
+        """Per-block sums with reduce3..6's index ranges (inc/testing.cuh:185-235)."""
+        a = _np(x, np.float32).ravel()
+        out = np.empty(n_blocks, dtype=np.float32)
+        _check(self._lib.mcb_reduce_blocks(self._h, a.ctypes.data if a.size else None, a.size, HOST, n_blocks, span,
+                                           1 if strided else 0, out.ctypes.data))
+        return out
+
+    def generate_normals(self, n, seed=1234):
+        out = np.empty(n, dtype=np.float32)
+        _check(self._lib.mcb_generate_normals(self._h, seed, n, out.ctypes.data if n else None, HOST))
+        return out
+
     def price_from_normals(self, opt, normals):
         z = _np(normals, np.float32)
         n_paths, n_steps = z.shape
@@ -320,6 +336,13 @@ class Engine:
         out = np.empty((SEGMENTS, 2), dtype=np.float64)
         _check(self._lib.mcb_last_segments(self._h, out.ctypes.data))
         return out
+
+
+def write_trajectories_csv(path, prices, x0, dt):
+    """testing.cu:37-47: ``time,trajectory,value`` with the t = 0 row injected per trajectory."""
+    a = _np(prices, np.float32)
+    n_traj, n_steps = a.shape
+    _check(load_library().mcb_write_trajectories_csv(os.fsencode(path), a.ctypes.data, n_traj, n_steps, x0, dt))
 
 
 # ---- shard arithmetic (pure host logic, mirrored from csrc/mcb200.cu segment_span) -----------

@@ -859,6 +859,66 @@ int mcb_reduce_sum(mcb_engine *e, const float *x, uint64_t n, int where, float *
     return MCB_OK;
 }
 
+int mcb_reduce_blocks(mcb_engine *e, const float *x, uint64_t n, int where, uint32_t n_blocks, uint64_t span,
+                      int strided, float *out)
+{
+    if (!e || !out || (!x && n)) return fail(MCB_ERR_INVALID, "NULL argument");
+    if (where != MCB_HOST && where != MCB_DEVICE) return fail(MCB_ERR_INVALID, "bad `where`");
+    if (n_blocks == 0 || n_blocks > 0x7fffffffu || span == 0) return fail(MCB_ERR_INVALID, "bad n_blocks / span");
+    DeviceGuard g(e->device);
+    int rc;
+    const size_t in_bytes = where == MCB_HOST ? (size_t)n * sizeof(float) : 0;
+    const size_t in_pad = (in_bytes + 255) & ~(size_t)255;
+    if ((rc = e->scratch.reserve(in_pad + (size_t)n_blocks * sizeof(float) + 16))) return rc;
+    const float *dx = x;
+    if (where == MCB_HOST) {
+        if (n) CU(cudaMemcpyAsync(e->scratch.ptr, x, in_bytes, cudaMemcpyHostToDevice, e->stream));
+        dx = reinterpret_cast<const float *>(e->scratch.ptr);
+    }
+    float *d_out = reinterpret_cast<float *>(e->scratch.ptr + in_pad);
+    reduce_blocks_kernel<<<n_blocks, kSlots, 0, e->stream>>>(dx, n, span, strided, d_out);
+    e->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, d_out, (size_t)n_blocks * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return MCB_OK;
+}
+
+int mcb_generate_normals(mcb_engine *e, uint64_t seed, uint64_t n, float *out, int where)
+{
+    if (!e || (!out && n)) return fail(MCB_ERR_INVALID, "NULL argument");
+    if (where != MCB_HOST && where != MCB_DEVICE) return fail(MCB_ERR_INVALID, "bad `where`");
+    if (n == 0) return MCB_OK;
+    if (where == MCB_HOST) return mcb_stream_normals(e, seed, 0, 0, n, out);
+    DeviceGuard g(e->device);
+    if ((n + 127) / 128 > 0x7fffffffull) return fail(MCB_ERR_INVALID, "too many normals for one launch");
+    stream_normals_kernel<<<(unsigned)((n + 127) / 128), 128, 0, e->stream>>>(make_philox_keys(seed), 0, 0, n, out);
+    e->launches++;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(e->stream));
+    return MCB_OK;
+}
+
+int mcb_write_trajectories_csv(const char *path, const float *prices, uint64_t n_trajectories, int n_steps, float x0,
+                               float dt)
+{
+    if (!path || (!prices && n_trajectories)) return fail(MCB_ERR_INVALID, "NULL argument");
+    if (n_steps < 1) return fail(MCB_ERR_INVALID, "n_steps must be >= 1");
+    FILE *f = fopen(path, "w");
+    if (!f) return fail(MCB_ERR_INVALID, "cannot open %s for writing", path);
+    // same text a C++ ostream prints for these floats (testing.cu:41-46 streams float values)
+    fprintf(f, "time,trajectory,value\n");
+    for (uint64_t p = 0; p < n_trajectories; ++p) {
+        fprintf(f, "0,%llu,%g\n", (unsigned long long)p, (double)x0);
+        for (int i = 0; i < n_steps; ++i)
+            fprintf(f, "%g,%llu,%g\n", (double)((float)(1 + i) * dt), (unsigned long long)p,
+                    (double)prices[p * (uint64_t)n_steps + (uint64_t)i]);
+    }
+    const bool bad = ferror(f) != 0;
+    if (fclose(f) != 0 || bad) return fail(MCB_ERR_INVALID, "write to %s failed", path);
+    return MCB_OK;
+}
+
 int mcb_price_from_normals(mcb_engine *e, const mcb_option_data *opt, const float *normals, uint64_t n_paths,
                            int n_steps, float *payoffs, int where)
 {

@@ -410,6 +410,22 @@ reduce_sum_kernel(const float *__restrict__ x, uint64_t n, float *__restrict__ o
     if (threadIdx.x == 0) out[0] = a;
 }
 
+// reduce3..6 index ranges, one CTA per "block" of the reference's launch (see mcb_reduce_blocks).
+__global__ void __launch_bounds__(kSlots)
+reduce_blocks_kernel(const float *__restrict__ x, uint64_t n, uint64_t span, int strided, float *__restrict__ out)
+{
+    __shared__ float scratch[2 * kWarps];
+    float a = 0.0f, b = 0.0f;
+    const uint64_t hop = strided ? (uint64_t)gridDim.x * span : ~0ull;
+    for (uint64_t lo = (uint64_t)blockIdx.x * span; lo < n; lo += hop) {
+        const uint64_t hi = lo + span < n ? lo + span : n;
+        for (uint64_t i = lo + threadIdx.x; i < hi; i += kSlots) a = a + x[i];
+        if (!strided) break;
+    }
+    block_fold2(a, b, scratch);
+    if (threadIdx.x == 0) out[blockIdx.x] = a;
+}
+
 // Pricing from pre-generated normals (inc/trajectories.cuh:14-52): thread per path.
 __global__ void __launch_bounds__(kSlots)
 pregen_kernel(const float *__restrict__ normals, uint64_t n_paths, int n_steps, float l0, float dr, float v,

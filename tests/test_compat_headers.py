@@ -24,17 +24,21 @@ def test_example_driver_builds(pkg):
     assert os.access(exe, os.X_OK)
 
 
-def test_reference_hello_cu_compiles_unchanged(tmp_path, pkg):
-    """the reference's own main() builds against the compat headers + the C-ABI."""
-    src = "/root/reference/hello.cu"
+@pytest.mark.parametrize("driver,symbols", [
+    ("hello", ("mcb_price_european", "mcb_price_bullet", "mcb_nested_monte_carlo", "mcb_engine_create")),
+    ("testing", ("mcb_simulate_trajectories", "mcb_reduce_blocks", "mcb_generate_normals")),
+])
+def test_reference_drivers_compile_unchanged(tmp_path, pkg, driver, symbols):
+    """the reference's own main()s build against the compat headers + the C-ABI."""
+    src = f"/root/reference/{driver}.cu"
     if not os.path.exists(src):
         pytest.skip("/root/reference is only present in the build container")
     import __graft_entry__ as entry
     entry._load_build_module().build()
-    exe = str(tmp_path / "hello_ref")
+    exe = str(tmp_path / f"{driver}_ref")
     _nvcc(src, exe)
     syms = subprocess.run(["nm", "-D", "--undefined-only", exe], capture_output=True, text=True, check=True).stdout
-    for name in ("mcb_price_european", "mcb_price_bullet", "mcb_nested_monte_carlo", "mcb_engine_create"):
+    for name in symbols:
         assert name in syms
 
 
@@ -78,3 +82,60 @@ def test_example_driver_runs_and_matches_the_python_surface(pkg, orc):
     opt = pkg.option(r=0.1, N_PATHS=100000, N_PATHS_INNER=64, N_STEPS=100)
     assert np.float32(gpu_v) == np.float32(pkg.wrapper_gpu_option_vanilla(opt, 1024, quiet=True))
     assert np.float32(gpu_b) == np.float32(pkg.wrapper_gpu_bullet_option(opt, 1024, quiet=True))
+
+
+@pytest.mark.gpu
+def test_testing_driver_runs(tmp_path, pkg, orc, engine):
+    """examples/testing_b200.cu: Simulation facade (pre-generated normals CPU vs GPU, the four
+    reductions, outer trajectories) and the CSV format of testing.cu:37-47."""
+    import __graft_entry__ as entry
+    entry.build_examples()
+    exe = os.path.join(ROOT, "build", "testing_b200")
+    csv_path = str(tmp_path / "testing.csv")
+    out = subprocess.run([exe, csv_path], capture_output=True, text=True, check=True).stdout
+    tag = lambda t: [ln.split()[1:] for ln in out.splitlines() if ln.startswith(t)]
+    n, worst = tag("PREGEN")[0]
+    # same normals; both sides accumulate 100 FP32 log-increments (CPU natural log, GPU log2), so they
+    # agree to ~100 * 2^-24 * ln(S) relative: < 2e-2 absolute on payoffs up to a few hundred
+    assert int(n) == 1024 and float(worst) < 2e-2
+    z = engine.generate_normals(1024 * 100, 1234)
+    red = {int(k): np.float32(v) for k, v in tag("REDUCE")}
+    first2048 = orc.reduce_sum_f32(z[:2048])
+    assert red[3] == red[4] == red[5] == first2048            # block 0 of reduce3/4/5 covers 2*1024 elements
+    # reduce6 grid-strides: with one block it covers everything, span by span through the same tree
+    assert red[6] == engine.reduce_blocks(z, 1, 2048, strided=True)[0]
+    assert abs(float(red[6]) - z.astype(np.float64).sum()) < 0.05
+    assert abs(float(tag("HOSTSUM")[0][0]) - z.astype(np.float64).sum()) < 0.5
+    # CSV: header, t = 0 row per trajectory, (1+i)*dt timestamps; byte-identical to the ostream rendering
+    text = open(csv_path).read()
+    assert text == open(csv_path + ".ostream").read()
+    lines = text.splitlines()
+    assert lines[0] == "time,trajectory,value" and len(lines) == 1 + 20 * 151
+    assert lines[1] == "0,0,100" and lines[2].startswith("0.00666667,0,")
+    rows = engine.simulate_trajectories(pkg.option(r=0.1, B=0.0, N_STEPS=150, N_PATHS=20, P1=0, P2=0), 0, 20, 555)
+    assert float(lines[2].split(",")[2]) == pytest.approx(float(rows[0, 0]), rel=1e-5)
+    assert float(lines[-1].split(",")[2]) == pytest.approx(float(rows[-1, -1]), rel=1e-5)
+
+
+@pytest.mark.gpu
+def test_reference_mains_run_on_the_new_engine():
+    """The reference's UNMODIFIED hello.cu / testing.cu, compiled in the build container against
+    include/compat (build/*_reference_main travel with the snapshot), run on the B200."""
+    hello = os.path.join(ROOT, "build", "hello_reference_main")
+    testing = os.path.join(ROOT, "build", "testing_reference_main")
+    if not (os.path.exists(hello) and os.path.exists(testing)):
+        pytest.skip("build/*_reference_main are built only where /root/reference exists")
+    out = subprocess.run([hello], capture_output=True, text=True, check=True, timeout=600).stdout
+    val = lambda label: float([ln for ln in out.splitlines() if ln.startswith(label)][0].split(":")[1])
+    bs = val("call Black Scholes")
+    assert bs == pytest.approx(13.2697, abs=1e-4)
+    assert abs(val("Average GPU ") - bs) < 0.25 and abs(val("Average CPU Vanilla Option") - bs) < 0.25
+    assert val("Average GPU bullet option ") == val("Average GPU bullet option atomic ")
+    nmc = [val("Average GPU bullet option nmc " + k) for k in ("one point per block", "one kernel", "optimal")]
+    assert nmc[0] == nmc[1] == nmc[2] and nmc[0] > 0
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        out = subprocess.run([testing], capture_output=True, text=True, check=True, cwd=d, timeout=600).stdout
+        assert "Testing reduction: 6" in out and "Total size: 3000" in out
+        lines = open(os.path.join(d, "testing.csv")).read().splitlines()
+        assert lines[0] == "time,trajectory,value" and len(lines) == 1 + 20 * 151
