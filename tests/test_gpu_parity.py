@@ -486,3 +486,46 @@ def test_device_info(engine):
     info = engine.device_info()
     assert info.cc_major == 10 and info.sm_count >= 100
     assert b"B200" in info.name or b"NVIDIA" in info.name
+
+
+# ------------------------------------------------------------- out-of-bounds canaries (no sanitizer on this pool)
+@pytest.mark.parametrize("n_steps,n_paths", [(252, 61), (252, 24), (256, 7), (100, 33), (128, 5), (7, 5), (300, 9),
+                                             (1, 3), (37, 1), (1024, 3)])
+def test_trajectory_kernels_stay_inside_their_buffers(engine, pkg, n_steps, n_paths):
+    """compute-sanitizer is closed on this pool, so bounds are checked with guard bands: the kernels
+    (TMA slab kernel for single-pass aligned rows, general kernel otherwise, with and without
+    counts) must write every element of [guard, guard + n) and nothing else."""
+    import torch
+    guard = 4096
+    n = n_steps * n_paths
+    opt = pkg.option(N_STEPS=n_steps, N_PATHS=n_paths, B=120.0)
+    for with_counts in (False, True):
+        prices = torch.full((n + 2 * guard,), float("nan"), dtype=torch.float32, device="cuda:0")
+        counts = torch.full((n + 2 * guard,), -7, dtype=torch.int32, device="cuda:0") if with_counts else None
+        engine.trajectories_async(opt, 11, n_paths, 1234, prices[guard:].data_ptr(),
+                                  counts[guard:].data_ptr() if with_counts else None)
+        engine.synchronize()
+        assert bool(torch.isnan(prices[:guard]).all()) and bool(torch.isnan(prices[guard + n:]).all())
+        assert bool(torch.isfinite(prices[guard:guard + n]).all())
+        if with_counts:
+            assert bool((counts[:guard] == -7).all()) and bool((counts[guard + n:] == -7).all())
+            assert bool((counts[guard:guard + n] >= 0).all())
+        host = engine.simulate_trajectories(opt, 11, n_paths, 1234)
+        assert (prices[guard:guard + n].cpu().numpy().view(np.uint32) == host.ravel().view(np.uint32)).all()
+
+
+def test_nested_and_segment_outputs_stay_inside_their_buffers(engine, pkg):
+    import torch
+    guard = 1024
+    opt = pkg.option(N_STEPS=13, N_PATHS=5, N_PATHS_INNER=300, B=120.0, P1=1, P2=10)
+    n = 13 * 5
+    F = torch.full((n + 2 * guard,), float("nan"), dtype=torch.float32, device="cuda:0")
+    engine.nested_async(opt, 2, 5, 1234, 1235, pkg.DISCOUNT_CORRECT, F[guard:].data_ptr())
+    engine.synchronize()
+    assert bool(torch.isnan(F[:guard]).all()) and bool(torch.isnan(F[guard + n:]).all())
+    assert bool(torch.isfinite(F[guard:guard + n]).all())
+    seg = torch.full((2 * pkg.SEGMENTS + 2 * guard,), float("nan"), dtype=torch.float64, device="cuda:0")
+    engine.european_segments_async(pkg.option(), 100001, 1234, pkg.CALL, 0, 1, seg[guard:].data_ptr())
+    engine.synchronize()
+    assert bool(torch.isnan(seg[:guard]).all()) and bool(torch.isnan(seg[guard + 2 * pkg.SEGMENTS:]).all())
+    assert bool(torch.isfinite(seg[guard:guard + 2 * pkg.SEGMENTS]).all())
