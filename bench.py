@@ -234,6 +234,8 @@ def run_b200(args):
         raise SystemExit("no CUDA device: this engine has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
+        # NCCL prints its version banner on stdout; stdout is reserved for the ONE JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     pkg = entry.load_package()
