@@ -118,13 +118,28 @@ enum { kStoreScalar = 0,   // any n_steps / alignment: 4-byte streaming stores
 // inclusive prefix, so step my_step + j ends at log2 price base + a[j].  carry_l (the log2 price
 // at the start of the pass) is advanced to the end of the pass.  Both trajectory kernels go
 // through this function, so a row's bits do not depend on which of them produced it.
+template <int SPL>
+struct PassWords {
+    Words4 w[SPL / 4];
+};
+
+// integer half of a pass: the Philox blocks of steps [my_step, my_step + SPL) of path (p_lo, p_hi)
+template <int SPL>
+__device__ __forceinline__ PassWords<SPL> row_words(const PathParams &prm, uint32_t p_lo, uint32_t p_hi, int my_step)
+{
+    PassWords<SPL> out;
+#pragma unroll
+    for (int b = 0; b < SPL / 4; ++b) out.w[b] = philox4x32_10((uint32_t)(my_step >> 2) + b, 0u, p_lo, p_hi, prm.keys);
+    return out;
+}
+
+// floating-point half: Box-Muller -> log2 increments -> in-lane prefix -> scan over the row's lanes
 template <int SPL, int LPR>
-__device__ __forceinline__ float row_pass(const PathParams &prm, uint32_t p_lo, uint32_t p_hi, int my_step,
-                                          bool active, float &carry_l, float (&a)[SPL])
+__device__ __forceinline__ float row_finish(const PathParams &prm, const PassWords<SPL> &words, bool active,
+                                            float &carry_l, float (&a)[SPL])
 {
 #pragma unroll
-    for (int b = 0; b < SPL / 4; ++b)
-        increments4(philox4x32_10((uint32_t)(my_step >> 2) + b, 0u, p_lo, p_hi, prm.keys), prm.sc, prm.dr, a + 4 * b);
+    for (int b = 0; b < SPL / 4; ++b) increments4(words.w[b], prm.sc, prm.dr, a + 4 * b);
 #pragma unroll
     for (int j = 1; j < SPL; ++j) a[j] = a[j] + a[j - 1];
     // lanes past the end of the row computed garbage (branch-free, the warp stays converged for
@@ -133,6 +148,13 @@ __device__ __forceinline__ float row_pass(const PathParams &prm, uint32_t p_lo, 
     const float base = carry_l + group_exclusive_scan<LPR>(lane_total);
     carry_l = __shfl_sync(kFullMask, base + lane_total, LPR - 1, LPR);
     return base;
+}
+
+template <int SPL, int LPR>
+__device__ __forceinline__ float row_pass(const PathParams &prm, uint32_t p_lo, uint32_t p_hi, int my_step,
+                                          bool active, float &carry_l, float (&a)[SPL])
+{
+    return row_finish<SPL, LPR>(prm, row_words<SPL>(prm, p_lo, p_hi, my_step), active, carry_l, a);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -259,12 +281,15 @@ trajectory_slab_kernel(const __grid_constant__ PathParams prm, float *__restrict
 #pragma unroll 1
     for (uint32_t slab = blockIdx.x * WARPS + warp; slab < n_slabs; slab += slab_stride) {
         const uint32_t slab_row = slab * ROWS;
+        // (Drawing the next pass's Philox blocks while this pass's Box-Muller / exp2 work is in
+        // flight was tried -- software pipelining -- and lost 15 % to register pressure.)
 #pragma unroll 1
         for (int r = 0; r < ROWS; r += kRowsPerWarp) {
             const uint64_t p = prm.first_path + slab_row + (uint32_t)(r + sub);   // rows past n_rows: computed, not copied
+            const PassWords<SPL> words = row_words<SPL>(prm, (uint32_t)p, (uint32_t)(p >> 32), my_step);
             float carry_l = prm.l0;
             float a[SPL];
-            const float base = row_pass<SPL, LPR>(prm, (uint32_t)p, (uint32_t)(p >> 32), my_step, active, carry_l, a);
+            const float base = row_finish<SPL, LPR>(prm, words, active, carry_l, a);
 #pragma unroll
             for (int j = 0; j < SPL; ++j) a[j] = mufu_ex2(base + a[j]);
             if (r == 0) {

@@ -64,7 +64,7 @@ __device__ __forceinline__ float european_payoff(uint32_t p_lo, uint32_t p_hi, c
 // One CTA = one chunk of kSlots * PPS consecutive paths.  Slot t (= thread t) accumulates
 // chunk-local paths t, t+256, ... in that order; partials[chunk - first_chunk] = (sum, sumsq).
 // payoffs (nullable) receives every path's payoff (parity hook).
-template <int TYPE, int PPS>
+template <int TYPE, int PPS, int UNROLL = 4>
 __global__ void __launch_bounds__(kSlots)
 european_kernel(const __grid_constant__ EuropeanParams prm, float2 *__restrict__ partials,
                 float *__restrict__ payoffs, uint64_t payoffs_first_path)
@@ -80,7 +80,7 @@ european_kernel(const __grid_constant__ EuropeanParams prm, float2 *__restrict__
     float sum = 0.0f, sq = 0.0f;
     if (left >= (uint64_t)(kSlots * PPS) && payoffs == nullptr) {
         uint64_t prod1 = (uint64_t)kPhiloxM1 * p_lo0;   // a chunk never wraps p_lo, so this stays M1 * p_lo
-#pragma unroll 4
+#pragma unroll UNROLL
         for (int i = 0; i < PPS; ++i) {
             const float pay = european_payoff_from_prod<TYPE>(prod1, p_hi, prm);
             prod1 += (uint64_t)kPhiloxM1 * kSlots;
