@@ -529,3 +529,62 @@ def test_nested_and_segment_outputs_stay_inside_their_buffers(engine, pkg):
     engine.synchronize()
     assert bool(torch.isnan(seg[:guard]).all()) and bool(torch.isnan(seg[guard + 2 * pkg.SEGMENTS:]).all())
     assert bool(torch.isfinite(seg[guard:guard + 2 * pkg.SEGMENTS]).all())
+
+
+# ------------------------------------------------------------------ BASELINE configs[3] / [4] at full size
+def test_sweep_full_size_config5(engine, orc, pkg):
+    """BASELINE configs[4] on one GPU: 1024 parameter sets (32 strikes x 32 vols) x 2^26 paths with
+    common random numbers.  Every set with enough in-the-money mass within 4 SE of the closed form;
+    prices monotone in the strike for every vol; a spot-checked set bit-identical to a separate
+    European call."""
+    n = 1 << 26
+    strikes = np.linspace(60, 140, 32, dtype=np.float32)
+    vols = np.linspace(0.05, 0.8, 32, dtype=np.float32)
+    K, V = np.meshgrid(strikes, vols, indexing="ij")
+    out = engine.price_sweep(pkg.option(**CFG1), K.ravel(), V.ravel(), n, 1234, pkg.CALL)
+    L = orc.lib()
+    price = np.array([r.price for r in out]).reshape(32, 32)
+    checked = 0
+    for i, (k, v) in enumerate(zip(K.ravel(), V.ravel())):
+        d2 = (np.log(100.0 / k) + (0.05 - 0.5 * v * v)) / v
+        if n * 0.5 * math.erfc(-d2 / np.sqrt(2.0)) < 1e5:
+            continue
+        exact = L.orc_bs_call_exact(100.0, float(k), 1.0, 0.05, float(v))
+        assert abs(out[i].price - exact) < 4.0 * out[i].std_error, (k, v, out[i].price, exact, out[i].std_error)
+        checked += 1
+    assert checked > 900
+    assert (np.diff(price, axis=0) <= 1e-9).all()            # call price decreases with the strike (same draws)
+    one = engine.price_european(pkg.option(S0=100.0, T=1.0, r=0.05, K=float(K[17, 9]), v=float(V[17, 9])), n, 1234)
+    assert out[17 * 32 + 9].sum == one.sum and out[17 * 32 + 9].sumsq == one.sumsq
+
+
+def test_nested_full_size_config4(engine, orc, pkg):
+    """BASELINE configs[3]: 4096 outer x 4096 inner x 100 steps (8.3e10 inner path-steps) on device
+    buffers.  Size-independent checks: F finite and >= 0; the last step is the gated intrinsic value;
+    rows re-run as a small job come back bit-identical (CTA p depends only on p); tower property:
+    the mean over outer paths of F[:, k] (compat discount = e^{-rT} for every k) is the time-0 bullet
+    price for every k, within 4 SE of its cross-sectional spread."""
+    import torch
+    n_out, n_in, steps = 4096, 4096, 100
+    opt = pkg.option(N_STEPS=steps, N_PATHS=n_out, N_PATHS_INNER=n_in, B=120.0, P1=10, P2=50, **CFG1)
+    F = torch.empty(n_out * steps, dtype=torch.float32, device="cuda:0")
+    P = torch.empty(n_out * steps, dtype=torch.float32, device="cuda:0")
+    Cn = torch.empty(n_out * steps, dtype=torch.int32, device="cuda:0")
+    engine.nested_async(opt, 0, n_out, 1234, 1235, pkg.DISCOUNT_COMPAT, F.data_ptr(), P.data_ptr(), Cn.data_ptr())
+    engine.synchronize()
+    Fh = F.view(n_out, steps).cpu().numpy().astype(np.float64)
+    Ph = P.view(n_out, steps).cpu().numpy()
+    Ch = Cn.view(n_out, steps).cpu().numpy()
+    assert np.isfinite(Fh).all() and (Fh >= 0).all()
+    gate = (Ch[:, -1] >= 10) & (Ch[:, -1] <= 50)
+    want_last = np.where(gate, np.maximum(Ph[:, -1] - 100.0, 0.0), 0.0) * np.exp(-0.05)
+    assert np.allclose(Fh[:, -1], want_last, rtol=1e-5, atol=1e-4)
+    small, _, _, _ = engine.nested_monte_carlo(pkg.option(N_STEPS=steps, N_PATHS=2, N_PATHS_INNER=n_in, B=120.0,
+                                                          P1=10, P2=50, **CFG1), 1000, 2, 1234, 1235,
+                                               pkg.DISCOUNT_COMPAT)
+    assert (small.view(np.uint32) == F.view(n_out, steps)[1000:1002].cpu().numpy().view(np.uint32)).all()
+    ref = engine.price_bullet(pkg.option(N_STEPS=steps, N_PATHS=1 << 22, B=120.0, P1=10, P2=50, **CFG1), 1 << 22, 99)
+    for k in (0, 10, 50, 90, 99):
+        col = Fh[:, k]
+        se = col.std() / np.sqrt(n_out)
+        assert abs(col.mean() - ref.price) < 4.0 * np.hypot(se, ref.std_error), (k, col.mean(), ref.price, se)
