@@ -56,6 +56,65 @@ __global__ void __launch_bounds__(256) probe(PhiloxKeys keys, float sc, float dr
     if (acc == 123.456f || xacc == 77u) sink[0] = acc;
 }
 
+// Specialisation experiment: warps 0-3 of a CTA run Philox-only passes, warps 4-7 run everything else
+// (Box-Muller, prefix, scan, exp2) on cheap integers -- no data exchange, just the two instruction
+// streams side by side on every SMSP.  Same total number of passes of each kind as the fused kernel.
+__global__ void __launch_bounds__(256) probe_split(PhiloxKeys keys, float sc, float dr, int passes, float *out, float *sink)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t pair = blockIdx.x * 4 + (warp & 3);
+    float acc = 0.0f;
+    uint32_t xacc = 0;
+    if (warp < 4) {
+        for (int r = 0; r < 2 * passes; ++r) {
+            const uint32_t p_lo = pair * 2 * passes + r;
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                const Words4 w = philox4x32_10((uint32_t)(2 * lane + b), 0u, p_lo, 0u, keys);
+                xacc ^= w.x ^ w.y ^ w.z ^ w.w;
+            }
+        }
+    } else {
+        float carry = 6.64f;
+        for (int r = 0; r < 2 * passes; ++r) {
+            const uint32_t p_lo = pair * 2 * passes + r;
+            float a[8];
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                Words4 w;
+                w.x = p_lo * 2654435761u + lane * 40503u + b; w.y = w.x * 2246822519u; w.z = w.y ^ (w.x >> 7); w.w = w.z * 3266489917u;
+                increments4(w, sc, dr, a + 4 * b);
+            }
+#pragma unroll
+            for (int j = 1; j < 8; ++j) a[j] = a[j] + a[j - 1];
+            float x = __shfl_up_sync(kFullMask, a[7], 1);
+            if (lane == 0) x = 0.0f;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) { float y = __shfl_up_sync(kFullMask, x, off); if (lane >= off) x += y; }
+            const float base = carry + x;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc += mufu_ex2(base + a[j]);
+        }
+    }
+    if (acc == 123.456f || xacc == 77u) sink[0] = acc + xacc;
+}
+
+void run_split(float *out, float *sink)
+{
+    const int passes = 8, blocks = (1 << 20) / passes / 8;
+    PhiloxKeys k = make_philox_keys(1234);
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    for (int i = 0; i < 3; ++i) probe_split<<<blocks, 256>>>(k, 0.0214f, 1.6e-4f, passes, out, sink);
+    cudaEventRecord(a);
+    for (int i = 0; i < 20; ++i) probe_split<<<blocks, 256>>>(k, 0.0214f, 1.6e-4f, passes, out, sink);
+    cudaEventRecord(b);
+    cudaEventSynchronize(b);
+    float ms; cudaEventElapsedTime(&ms, a, b); ms /= 20;
+    printf("%-44s %8.1f us  %6.3f Tsteps/s  %s\n", "SPLIT: int warps || fp warps (no exchange)", ms * 1e3,
+           (double)(1 << 20) * 256 / ms / 1e9, cudaGetErrorString(cudaGetLastError()));
+}
+
 template <int WHAT>
 void run(const char *name, float *out, float *sink)
 {
@@ -87,6 +146,7 @@ int main()
     run<PHILOX | BOXMULLER | PREFIX | SCAN | EXP2 | STORE>("+ stores (full)", out, sink);
     run<PHILOX | BOXMULLER | PREFIX | EXP2 | STORE>("full without scan", out, sink);
     run<BOXMULLER | PREFIX | SCAN | EXP2 | STORE>("full without philox", out, sink);
+    run_split(out, sink);
     run<STORE>("stores only", out, sink);
     run<EXP2 | STORE>("ex2 + stores", out, sink);
     return 0;
