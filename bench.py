@@ -421,7 +421,10 @@ def other_workloads(torch, pkg, eng, hbm_gbs, peak_src):
     ob = pkg.option(N_STEPS=100, N_PATHS=1 << 22, B=120.0, P1=10, P2=50, **CFG)
     seg = torch.zeros(2 * pkg.SEGMENTS, dtype=torch.float64, device="cuda")
     t = timed(lambda: eng.bullet_segments_async(ob, 1 << 22, SEED, 0, 0.0, 0, 0, 1, seg.data_ptr(), stream), 10)
-    out["bullet_2^22x100"] = {"path_steps_per_s": (1 << 22) * 100 / t, "ms": 1e3 * t}
+    walk_bound = 148 * 30.0 * 1.965e9 / 4.75   # fmaheavy: ~4.75 IMAD.WIDE per step at ~30 /clk/SM (measured)
+    out["bullet_2^22x100"] = {"path_steps_per_s": (1 << 22) * 100 / t, "ms": 1e3 * t,
+                              "bound": "fmaheavy: 4.75 IMAD.WIDE per path-step at 30/clk/SM (measured) = 1.84e12 /s",
+                              "frac": (1 << 22) * 100 / t / walk_bound}
 
     # configs[3]: nested MC 4096 outer x 4096 inner x 100 steps = 8.30e10 inner path-steps
     on = pkg.option(N_STEPS=100, N_PATHS=4096, N_PATHS_INNER=4096, B=120.0, P1=10, P2=50, **CFG)
@@ -431,6 +434,7 @@ def other_workloads(torch, pkg, eng, hbm_gbs, peak_src):
     inner_steps = 4096 * 4096 * sum(99 - k for k in range(100))
     out["nested_4096x4096x100"] = {"inner_path_steps_per_s_upper": inner_steps / t, "ms": 1e3 * t,
                                    "note": "upper = no early-out assumed; points with count > P2 are skipped",
+                                   "bound": "fmaheavy, as bullet", "frac_upper": inner_steps / t / walk_bound,
                                    "mean_F": float(F.double().mean())}
 
     # configs[4]: 1024 parameter sets x 2^26 paths (whole job on this one GPU)
@@ -443,7 +447,8 @@ def other_workloads(torch, pkg, eng, hbm_gbs, peak_src):
     t = timed(lambda: eng.sweep_segments_async(os_, k, v, 1 << 26, SEED, pkg.CALL, 0, 1, segs.data_ptr(), stream),
               3, warm=1)
     out["sweep_1024x2^26"] = {"path_params_per_s": 1024 * (1 << 26) / t, "ms": 1e3 * t,
-                              "bound": "XU: one MUFU.EX2 per (path, set) -> 16/clk/SM = 4.65e12 /s"}
+                              "bound": "XU: one MUFU.EX2 per (path, set) -> 16/clk/SM = 4.65e12 /s",
+                              "frac": 1024 * (1 << 26) / t / (148 * 16 * 1.965e9)}
     return roofline_traj, out
 
 

@@ -146,6 +146,10 @@ int main()
     run<PHILOX | BOXMULLER | PREFIX | SCAN | EXP2 | STORE>("+ stores (full)", out, sink);
     run<PHILOX | BOXMULLER | PREFIX | EXP2 | STORE>("full without scan", out, sink);
     run<BOXMULLER | PREFIX | SCAN | EXP2 | STORE>("full without philox", out, sink);
+    run<BOXMULLER | PREFIX>("fp only: bm + prefix", out, sink);
+    run<BOXMULLER | PREFIX | SCAN>("fp only: bm + prefix + scan", out, sink);
+    run<BOXMULLER | PREFIX | EXP2>("fp only: bm + prefix + ex2 (no scan)", out, sink);
+    run<BOXMULLER | PREFIX | SCAN | EXP2>("fp only: bm + prefix + scan + ex2", out, sink);
     run_split(out, sink);
     run<STORE>("stores only", out, sink);
     run<EXP2 | STORE>("ex2 + stores", out, sink);
