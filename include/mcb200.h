@@ -203,6 +203,12 @@ int mcb_philox_blocks(mcb_engine *e, uint64_t seed, const uint64_t *subsequences
  * (curand_init(seed, subsequence, 4*block) + curand4): the live oracle of SURVEY.md 8(c). */
 int mcb_curand_blocks(mcb_engine *e, uint64_t seed, const uint64_t *subsequences, const uint64_t *blocks,
                       uint64_t n, uint32_t *words);
+/* Exhaustive accuracy scan of the engine's MUFU Box-Muller pieces against double precision over
+ * the 32-bit words [first_word, first_word + count): which = 0 radius sqrt(-2 ln u(x)), 1 sin of
+ * the angle v(y), 2 cos.  Returns the largest absolute error and the number of non-finite (or,
+ * for the radius, negative) results.  count = 2^32 covers every possible word. */
+int mcb_boxmuller_scan(mcb_engine *e, int which, uint64_t first_word, uint64_t count, double *max_abs_error,
+                       uint64_t *n_bad);
 /* The engine's float normals n0..n0+count-1 of one stream (host array out). */
 int mcb_stream_normals(mcb_engine *e, uint64_t seed, uint64_t subsequence, uint64_t n0, uint64_t count,
                        float *normals);

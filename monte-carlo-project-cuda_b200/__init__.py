@@ -118,6 +118,7 @@ SIGNATURES = {
     "mcb_timing_read": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_double), C.POINTER(_u64)]),
     "mcb_philox_blocks": (C.c_int, [_vp, _u64, _vp, _vp, _u64, _vp]),
     "mcb_curand_blocks": (C.c_int, [_vp, _u64, _vp, _vp, _u64, _vp]),
+    "mcb_boxmuller_scan": (C.c_int, [_vp, C.c_int, _u64, _u64, C.POINTER(C.c_double), C.POINTER(_u64)]),
     "mcb_stream_normals": (C.c_int, [_vp, _u64, _u64, _u64, _u64, _vp]),
     "mcb_european_payoffs": (C.c_int, [_vp, _OP, _u64, _u64, _u64, C.c_int, _vp]),
     "mcb_european_chunk_partials": (C.c_int, [_vp, _OP, _u64, _u64, C.c_int, _vp, _u64]),
@@ -307,6 +308,13 @@ class Engine:
         fn = self._lib.mcb_curand_blocks if library else self._lib.mcb_philox_blocks
         _check(fn(self._h, seed, s.ctypes.data, b.ctypes.data, s.size, out.ctypes.data))
         return out
+
+    def boxmuller_scan(self, which, first_word=0, count=1 << 32):
+        """(max |err| vs double, number of bad results) of the radius (0) / sin (1) / cos (2) map."""
+        err = C.c_double()
+        bad = _u64()
+        _check(self._lib.mcb_boxmuller_scan(self._h, which, first_word, count, C.byref(err), C.byref(bad)))
+        return err.value, int(bad.value)
 
     def stream_normals(self, seed, subsequence, count, n0=0):
         out = np.empty(count, dtype=np.float32)

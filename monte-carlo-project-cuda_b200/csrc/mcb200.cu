@@ -989,6 +989,29 @@ int mcb_curand_blocks(mcb_engine *e, uint64_t seed, const uint64_t *subsequences
     return blocks_hook(e, seed, subsequences, blocks, n, words, true);
 }
 
+int mcb_boxmuller_scan(mcb_engine *e, int which, uint64_t first_word, uint64_t count, double *max_abs_error,
+                       uint64_t *n_bad)
+{
+    if (!e || !max_abs_error || !n_bad) return fail(MCB_ERR_INVALID, "NULL argument");
+    if (which < 0 || which > 2) return fail(MCB_ERR_INVALID, "which must be 0 (radius), 1 (sin) or 2 (cos)");
+    DeviceGuard g(e->device);
+    int rc;
+    if ((rc = e->scratch.reserve(16))) return rc;
+    unsigned long long *d = reinterpret_cast<unsigned long long *>(e->scratch.ptr);
+    CU(cudaMemsetAsync(d, 0, 16, e->stream));
+    if (count) {
+        boxmuller_scan_kernel<<<e->prop.multiProcessorCount * 8, 256, 0, e->stream>>>(which, first_word, count, d);
+        e->launches++;
+        CU(cudaGetLastError());
+    }
+    unsigned long long h[2] = {0, 0};
+    CU(cudaMemcpyAsync(h, d, 16, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    memcpy(max_abs_error, &h[0], sizeof(double));
+    *n_bad = h[1];
+    return MCB_OK;
+}
+
 int mcb_stream_normals(mcb_engine *e, uint64_t seed, uint64_t subsequence, uint64_t n0, uint64_t count, float *normals)
 {
     if (!e || !normals) return fail(MCB_ERR_INVALID, "NULL argument");

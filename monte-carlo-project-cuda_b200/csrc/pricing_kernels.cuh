@@ -440,6 +440,41 @@ pregen_kernel(const float *__restrict__ normals, uint64_t n_paths, int n_steps, 
 }
 
 // ---- parity hooks ---------------------------------------------------------------------
+// Exhaustive accuracy scan of the MUFU Box-Muller pieces against double precision over a range
+// of 32-bit words: which == 0 -> radius s = sqrt(-2 ln u(x)); 1 -> sin v(y); 2 -> cos v(y).
+// out[0] = max |err| (as double bits via atomicMax on the ordered-int image), out[1] = number of
+// non-finite or (radius) negative results.
+__global__ void __launch_bounds__(256)
+boxmuller_scan_kernel(int which, uint64_t first, uint64_t count, unsigned long long *__restrict__ out)
+{
+    double worst = 0.0;
+    unsigned long long bad = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t w = (uint32_t)(first + i);
+        float got;
+        double want;
+        if (which == 0) {
+            got = kSqrt2Ln2 * bm_radius_unscaled(w);
+            const double u = (double)fmaf(__uint2float_rn(w), k2Pow32Inv, 0.5f * k2Pow32Inv);
+            want = sqrt(-2.0 * log(u));
+            if (!(got >= 0.0f)) ++bad;
+        } else {
+            const float v = bm_angle(w);
+            got = which == 1 ? mufu_sin(v) : mufu_cos(v);
+            // the oracle's angle: cuRAND's unsigned map, the same angle modulo 2 pi
+            const double vu = (double)fmaf(__uint2float_rn(w), k2Pow32Inv2Pi, 0.5f * k2Pow32Inv2Pi);
+            want = which == 1 ? sin(vu) : cos(vu);
+        }
+        if (!isfinite(got)) ++bad;
+        const double err = fabs((double)got - want);
+        worst = err > worst ? err : worst;
+    }
+    // non-negative doubles order like their bit patterns
+    atomicMax(out, (unsigned long long)__double_as_longlong(worst));
+    if (bad) atomicAdd(out + 1, bad);
+}
+
+
 __global__ void philox_blocks_kernel(PhiloxKeys keys, const uint64_t *__restrict__ subseq,
                                      const uint64_t *__restrict__ block, uint64_t n, uint4 *__restrict__ out)
 {

@@ -588,3 +588,21 @@ def test_nested_full_size_config4(engine, orc, pkg):
         col = Fh[:, k]
         se = col.std() / np.sqrt(n_out)
         assert abs(col.mean() - ref.price) < 4.0 * np.hypot(se, ref.std_error), (k, col.mean(), ref.price, se)
+
+
+def test_boxmuller_maps_exhaustively(engine):
+    """Every one of the 2^32 possible words through the MUFU radius / sin / cos maps against double
+    precision: no NaN, no negative radius (log(0) cannot happen: u in (0, 1]), and the worst-case
+    absolute errors that the per-normal tolerances above are derived from.
+      radius: MUFU.LG2 absolute error 2^-22 on log2 u blows up as 1.7e-7 / s near u -> 1, where
+              s -> 0; the largest error is therefore at the smallest non-zero radius (~3.5e-4);
+      sin/cos: MUFU on [-pi, pi) plus the FP32 angle, <= ~1e-6."""
+    err_r, bad_r = engine.boxmuller_scan(0)
+    err_s, bad_s = engine.boxmuller_scan(1)
+    err_c, bad_c = engine.boxmuller_scan(2)
+    assert bad_r == 0 and bad_s == 0 and bad_c == 0
+    assert err_r < 4e-4, err_r
+    assert err_s < 1.5e-6 and err_c < 1.5e-6, (err_s, err_c)
+    # away from u -> 1 (x < 2^32 - 2^24, i.e. s > ~0.09) the radius is good to ~2e-6
+    err_bulk, _ = engine.boxmuller_scan(0, 0, (1 << 32) - (1 << 24))
+    assert err_bulk < 3e-6, err_bulk
