@@ -573,6 +573,7 @@ int mcb_sweep_segments_async(mcb_engine *e, const mcb_option_data *opt, const fl
     // within a group ONE launch draws every path once and walks all the sets (sweep_kernel).
     uint64_t group = local ? (uint64_t)(8u << 20) / local : (uint64_t)n_params;
     if (group < 1) group = 1;
+    if (group > 65535) group = 65535;   // segment_kernel puts the parameter set on gridDim.y
     if (group > (uint64_t)n_params) group = (uint64_t)n_params;
     const uint64_t stride = local + 1;
     if ((rc = e->partials.reserve((size_t)(group * stride)))) return rc;

@@ -606,3 +606,15 @@ def test_boxmuller_maps_exhaustively(engine):
     # away from u -> 1 (x < 2^32 - 2^24, i.e. s > ~0.09) the radius is good to ~2e-6
     err_bulk, _ = engine.boxmuller_scan(0, 0, (1 << 32) - (1 << 24))
     assert err_bulk < 3e-6, err_bulk
+
+
+def test_sweep_with_more_sets_than_a_grid_dimension(engine, pkg):
+    """70 000 parameter sets on a tiny path count: the sets are priced in groups (gridDim.y <= 65535)."""
+    n_sets = 70_000
+    k = np.linspace(50, 150, n_sets, dtype=np.float32)
+    v = np.full(n_sets, 0.2, dtype=np.float32)
+    out = engine.price_sweep(pkg.option(**CFG1), k, v, 5000, 1234, pkg.CALL)
+    assert len(out) == n_sets
+    for i in (0, 1, 65534, 65535, 65536, n_sets - 1):
+        one = engine.price_european(pkg.option(S0=100.0, T=1.0, r=0.05, K=float(k[i]), v=0.2), 5000, 1234, pkg.CALL)
+        assert out[i].sum == one.sum and out[i].sumsq == one.sumsq
