@@ -314,14 +314,14 @@ int mcb_engine_create(int device, mcb_engine **out)
                     minor);
     }
     if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
-    if (err == cudaSuccess) err = cudaMallocHost(&e->h_segments, sizeof(double) * 2 * MCB_SEGMENTS);
+    if (err == cudaSuccess) err = cudaMallocHost(&e->h_segments, sizeof(double) * (2 * MCB_SEGMENTS + 8));
     if (err != cudaSuccess) {
         int rc = fail(MCB_ERR_CUDA, "engine setup failed: %s", cudaGetErrorString(err));
         mcb_engine_destroy(e);
         return rc;
     }
-    memset(e->h_segments, 0, sizeof(double) * 2 * MCB_SEGMENTS);
-    if (e->segments.reserve(2 * MCB_SEGMENTS) || reserve_results(e, 1)) {
+    memset(e->h_segments, 0, sizeof(double) * (2 * MCB_SEGMENTS + 8));
+    if (e->segments.reserve(2 * MCB_SEGMENTS + 8) || reserve_results(e, 1)) {
         mcb_engine_destroy(e);
         return MCB_ERR_NOMEM;
     }
@@ -453,8 +453,23 @@ int mcb_combine_segments_async(mcb_engine *e, const double *d_segments, int n_se
 
 static int finish_whole_job(mcb_engine *e, int n_sets, uint64_t n_paths, float r, float T, mcb_result *out)
 {
-    int rc = reserve_results(e, (size_t)n_sets);
-    if (rc) return rc;
+    int rc;
+    if (n_sets == 1) {
+        // single job (the reference's wrapper-sized calls): the result lands right behind the 64
+        // segments, so ONE small D2H copy brings both back (a 1e6-path call is ~40 us end to end,
+        // all of it launch + copy latency)
+        static_assert(sizeof(mcb_result) == 5 * sizeof(double), "mcb_result is five 8-byte fields");
+        double *d_job = e->segments.ptr;   // reserved to >= 2*MCB_SEGMENTS + 8 doubles at engine creation
+        if ((rc = mcb_combine_segments_async(e, d_job, 1, n_paths, r, T,
+                                             reinterpret_cast<mcb_result *>(d_job + 2 * MCB_SEGMENTS), nullptr)))
+            return rc;
+        CU(cudaMemcpyAsync(e->h_segments, d_job, sizeof(double) * (2 * MCB_SEGMENTS + 5), cudaMemcpyDeviceToHost,
+                           e->stream));
+        CU(cudaStreamSynchronize(e->stream));
+        memcpy(out, e->h_segments + 2 * MCB_SEGMENTS, sizeof(mcb_result));
+        return MCB_OK;
+    }
+    if ((rc = reserve_results(e, (size_t)n_sets))) return rc;
     if ((rc = mcb_combine_segments_async(e, e->segments.ptr, n_sets, n_paths, r, T,
                                          reinterpret_cast<mcb_result *>(e->results.ptr), nullptr)))
         return rc;
