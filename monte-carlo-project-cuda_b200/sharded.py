@@ -106,3 +106,35 @@ class ShardedPricer:
         with self.torch.cuda.stream(self.stream):
             self.sweep_async(opt, strikes, vols, n_paths, seed, option_type)
             return self._fetch(len(strikes))
+
+    # ---- slab-sharded modes: no collective on the data path --------------------------------
+    def trajectories_local(self, opt, n_paths, seed=1234, d_prices=None, d_counts=None):
+        """This rank's contiguous slab of the n_paths trajectories: returns (first_path, n_local,
+        prices tensor [n_local, N_STEPS] on this GPU).  Row p is a pure function of (seed, p), so the
+        concatenation over ranks is bit-identical to a single-GPU run."""
+        t = self.torch
+        lo, hi = path_span(self.rank, self.world, n_paths)
+        n_local = hi - lo
+        if d_prices is None:
+            d_prices = t.empty((max(n_local, 1), opt.N_STEPS), dtype=t.float32, device=self.device)
+        if n_local:
+            with t.cuda.stream(self.stream):
+                self.engine.trajectories_async(opt, lo, n_local, seed, d_prices.data_ptr(),
+                                               d_counts.data_ptr() if d_counts is not None else None, self._stream())
+        return lo, n_local, d_prices[:n_local]
+
+    def nested_local(self, opt, n_outer, seed_outer=1234, seed_inner=1235, discount_mode=0):
+        """This rank's slab of outer trajectories of a nested Monte Carlo: (first_outer, n_local,
+        F tensor [n_local, N_STEPS]).  Outer path p and all its inner paths depend on p only."""
+        t = self.torch
+        lo, hi = path_span(self.rank, self.world, n_outer)
+        n_local = hi - lo
+        F = t.empty((max(n_local, 1), opt.N_STEPS), dtype=t.float32, device=self.device)
+        if n_local:
+            with t.cuda.stream(self.stream):
+                self.engine.nested_async(opt, lo, n_local, seed_outer, seed_inner, discount_mode, F.data_ptr(),
+                                         None, None, self._stream())
+        return lo, n_local, F[:n_local]
+
+    def synchronize(self):
+        self.stream.synchronize()

@@ -41,6 +41,13 @@ def _worker(rank, world, port, out_dir):
         np.save(os.path.join(out_dir, f"r{rank}.npy"),
                 np.array([res.sum, res.sumsq, res.price, put.sum, bul.sum, bul.sumsq] + [x.sum for x in sw]))
         np.save(os.path.join(out_dir, f"rows{rank}.npy"), rows)
+        # the same through the sharded helper, and a nested-MC slab
+        lo2, n2, dev_rows = pricer.trajectories_local(pkg.option(N_STEPS=64, N_PATHS=1000), 1000, 1234)
+        nm = pkg.option(N_STEPS=12, N_PATHS=20, N_PATHS_INNER=128, B=120.0, P1=1, P2=10)
+        lo3, n3, F = pricer.nested_local(nm, 20, 1234, 1235, pkg.DISCOUNT_CORRECT)
+        pricer.synchronize()
+        assert (lo2, n2) == (lo, hi - lo) and (dev_rows.cpu().numpy().view(np.uint32) == rows.view(np.uint32)).all()
+        np.save(os.path.join(out_dir, f"F{rank}.npy"), F.cpu().numpy())
         eng.close()
     finally:
         dist.destroy_process_group()
@@ -71,3 +78,7 @@ def test_nccl_sharded_prices_match_single_gpu_bits(tmp_path, pkg, engine):
         assert (got == want).all(), (r, got, want)          # bit-identical on every rank
         got_rows.append(np.load(tmp_path / f"rows{r}.npy"))
     assert (np.concatenate(got_rows).view(np.uint32) == rows.view(np.uint32)).all()
+    nm = pkg.option(N_STEPS=12, N_PATHS=20, N_PATHS_INNER=128, B=120.0, P1=1, P2=10)
+    F, _, _, _ = engine.nested_monte_carlo(nm, 0, 20, 1234, 1235, pkg.DISCOUNT_CORRECT)
+    got_F = np.concatenate([np.load(tmp_path / f"F{r}.npy") for r in range(world)])
+    assert (got_F.view(np.uint32) == F.view(np.uint32)).all()
