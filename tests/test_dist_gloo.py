@@ -68,3 +68,37 @@ def test_sharded_combine_is_bit_identical(tmp_path, world, orc, pkg):
         assert g[0] == s and g[1] == q      # bit-identical on every rank, for every world size
     ds, _ = orc.european(o, 0, n_paths, 1234, orc.CALL)
     assert s == pytest.approx(ds, rel=1e-6)
+
+
+def _slab_worker(rank, world, port, n_paths, out_dir):
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as entry
+    import oracle
+    pkg = entry.load_package()
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        lo, hi = pkg.path_span(rank, world, n_paths)
+        o = oracle.option(N_STEPS=16, N_PATHS=n_paths, B=120.0)
+        prices, counts = oracle.trajectories(o, lo, hi - lo, 1234)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (lo, prices, counts))   # convenience gather; the data path needs none
+        if rank == 0:
+            gathered.sort(key=lambda t: t[0])
+            np.save(os.path.join(out_dir, "prices.npy"), np.concatenate([g[1] for g in gathered]))
+            np.save(os.path.join(out_dir, "counts.npy"), np.concatenate([g[2] for g in gathered]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_trajectory_slabs_concatenate_to_the_single_rank_result(tmp_path, world, orc):
+    """Trajectory mode / nested MC shard by contiguous path slabs with NO collective: row p depends on
+    (seed, p) only, so the ranks' slabs concatenate to exactly the single-rank array."""
+    n_paths = 37
+    port = 31500 + (os.getpid() % 2000) + world
+    mp.spawn(_slab_worker, args=(world, port, n_paths, str(tmp_path)), nprocs=world, join=True)
+    prices, counts = orc.trajectories(orc.option(N_STEPS=16, N_PATHS=n_paths, B=120.0), 0, n_paths, 1234)
+    assert (np.load(tmp_path / "prices.npy").view(np.uint32) == prices.view(np.uint32)).all()
+    assert (np.load(tmp_path / "counts.npy") == counts).all()
