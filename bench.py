@@ -245,7 +245,8 @@ def run_b200(args):
     pricer = sharded.ShardedPricer(eng)
     hbm_gbs, sm_max_mhz, peak_src = measured_peaks()
 
-    n_total = PATHS_PER_GPU * world
+    strong = args.scaling == "strong"
+    n_total = PATHS_PER_GPU if strong else PATHS_PER_GPU * world
     opt = pkg.option(N_PATHS=PATHS_PER_GPU, **CFG)
     sampler = ClockSampler(local)
     sampler.start()
@@ -312,10 +313,11 @@ def run_b200(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"European call S0=100 K=100 r=0.05 sigma=0.2 T=1, single step, 2^30 paths per GPU "
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"European call S0=100 K=100 r=0.05 sigma=0.2 T=1, single step, "
+                               f"{'2^30 paths in total' if strong else '2^30 paths per GPU'} "
                                f"({n_total} paths total), seed {SEED}, Philox4x32-10 keyed by (seed, path id)",
-                   "paths_per_gpu": PATHS_PER_GPU, "parallelism": f"path-index shards x{world}, one allreduce of 1 KiB",
+                   "paths_per_gpu": n_total // world, "parallelism": f"path-index shards x{world}, one allreduce of 1 KiB",
                    "l2": "n/a: the kernel reads no global memory (64 Ki chunk partials of 8 B written per launch)",
                    **CFG},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -328,7 +330,7 @@ def run_b200(args):
     }
     if kern_n:
         per_launch_s = kern_ms * 1e-3 / kern_n
-        paths_per_launch = PATHS_PER_GPU  # this rank's shard: n_total / world
+        paths_per_launch = n_total / world  # this rank's shard
         achieved = INSTR_PER_EUROPEAN_PATH * paths_per_launch / per_launch_s / 1e12
         sms = eng.device_info().sm_count
         peak = sms * ISSUE_PER_CLK_PER_SM * sm_max_mhz * 1e6 / 1e12
@@ -476,6 +478,8 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default): 2^30 paths per GPU; strong: 2^30 paths in total")
     ap.add_argument("--headline-only", action="store_true", help="skip the other BASELINE configs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
