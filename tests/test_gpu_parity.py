@@ -618,3 +618,27 @@ def test_sweep_with_more_sets_than_a_grid_dimension(engine, pkg):
     for i in (0, 1, 65534, 65535, 65536, n_sets - 1):
         one = engine.price_european(pkg.option(S0=100.0, T=1.0, r=0.05, K=float(k[i]), v=0.2), 5000, 1234, pkg.CALL)
         assert out[i].sum == one.sum and out[i].sumsq == one.sumsq
+
+
+def test_gpu_prices_agree_with_the_reference_cpu_path(engine, orc, pkg):
+    """north_star: "prices agree with the reference's CPU path ... within 3 standard errors".  The
+    UNMODIFIED reference CPU pricers (oracle/_ref, inc/tool.cuh:104-173) are unseeded, so the
+    comparison is statistical: 8 reference runs of 2^20 paths against the engine's 2^26-path price
+    (whose own SE is negligible next to the reference's).  The reference seeds from random_device, so
+    the bound used is 4 SE (a 3 SE bound would fail one honest run in ~200)."""
+    if not orc.have_ref():
+        pytest.skip("oracle/_ref is built only where /root/reference exists")
+    ref = orc.ref_cpu()
+    n_ref, runs = 1 << 20, 8
+    # vanilla (hello.cu parameters, r = 0.1)
+    o = orc.option(r=0.1, N_PATHS=n_ref)
+    prices = np.array([ref.ref_vanilla_cpu(C.byref(o)) for _ in range(runs)], dtype=np.float64)
+    gpu = engine.price_european(pkg.option(r=0.1), 1 << 26, 1234, pkg.CALL)
+    se_ref = gpu.std_error * np.sqrt((1 << 26) / (n_ref * runs))     # SE of the pooled reference mean
+    assert abs(prices.mean() - gpu.price) < 4.0 * np.hypot(se_ref, gpu.std_error) + 2e-3, (prices, gpu)
+    # bullet (hello.cu parameters)
+    ob = orc.option(r=0.1, B=120.0, P1=10, P2=50, N_STEPS=100, N_PATHS=1 << 17)
+    bp = np.array([ref.ref_bullet_cpu(C.byref(ob)) for _ in range(runs)], dtype=np.float64)
+    gb = engine.price_bullet(pkg.option(r=0.1, B=120.0, P1=10, P2=50, N_STEPS=100), 1 << 22, 1234)
+    se_b = gb.std_error * np.sqrt((1 << 22) / ((1 << 17) * runs))
+    assert abs(bp.mean() - gb.price) < 4.0 * np.hypot(se_b, gb.std_error) + 2e-3, (bp, gb)
