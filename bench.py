@@ -174,6 +174,28 @@ def reference_rate(threads: int, paths_per_thread: int, chunk: int = 1 << 20):
     return threads * paths_per_thread / dt, dt, sum(out) / threads, kind
 
 
+def reference_gpu_baseline(n_paths: int = 1 << 26):
+    """The UNMODIFIED reference GPU wrappers (oracle/_ref/ref_gpu: inc/wrappers.cuh:33-93 compiled for
+    sm_100 in the build container) timed on this GPU as a caller experiences them -- cudaMalloc of
+    the XORWOW states, setup_kernel, pricing kernel, sync, copy, free.  A reported baseline like
+    cpu_baseline; None when the executable did not travel."""
+    import subprocess
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_gpu")
+    if not os.path.exists(exe):
+        return None
+    try:
+        out = subprocess.run([exe, str(n_paths), str(CFG["r"])], capture_output=True, text=True, timeout=120)
+        price = [ln.split() for ln in out.stdout.splitlines() if ln.startswith("REFGPU ")][0]
+        tm = [ln.split() for ln in out.stdout.splitlines() if ln.startswith("REFGPU_TIME")][0]
+        n = int(tm[1])
+        return {"kind": "reference", "what": "wrapper_gpu_option_vanilla / wrapper_gpu_bullet_option (100 steps), wall "
+                "clock of the whole wrapper call", "n_paths": n, "european_paths_per_s": n / float(tm[2]),
+                "bullet_path_steps_per_s": n * 100 / float(tm[3]), "european_price": float(price[2]),
+                "bullet_price": float(price[3])}
+    except Exception as exc:
+        return {"error": repr(exc)}
+
+
 def host_threads():
     try:
         return max(1, len(os.sched_getaffinity(0)))
@@ -373,6 +395,12 @@ def run_b200(args):
             "sample": f"{threads} threads x {per_thread} paths ({dt:.1f} s) of the 2^30-path workload, "
                       f"calls of 2^20 paths", "value_1core": rate1, "price": price,
         }
+
+    # ---- the reference's own GPU wrappers on this same GPU (rank 0, N = 1 only; context, not a target) ----
+    if world == 1 and rank == 0 and not args.no_cpu_baseline:
+        ref_gpu = reference_gpu_baseline()
+        if ref_gpu:
+            line["reference_gpu_baseline"] = ref_gpu
 
     if rank == 0:
         print(json.dumps(line), flush=True)
