@@ -456,7 +456,22 @@ def other_workloads(torch, pkg, eng, hbm_gbs, peak_src):
                      "l2": "output 1.06 GB per launch, larger than L2"}
     out["trajectories_2^20x252"] = {"path_steps_per_s": TRAJ_PATHS * TRAJ_STEPS / t, "GB_per_s": nbytes / t / 1e9,
                                     "ms": 1e3 * t}
-    del buf
+    # the reference's simulate_outer_trajectories (inc/trajectories.cuh:273-351) stores the barrier count next
+    # to every price: 8 B per path-step
+    cnt = torch.empty(TRAJ_PATHS * TRAJ_STEPS, dtype=torch.int32, device="cuda")
+    eng.timing_read(pkg.KERNEL_TRAJECTORY)
+    eng.timing_enable(True)
+    t2 = timed(lambda: eng.trajectories_async(opt, 0, TRAJ_PATHS, SEED, buf.data_ptr(), cnt.data_ptr(), stream), 30)
+    eng.timing_enable(False)
+    kms2, kn2 = eng.timing_read(pkg.KERNEL_TRAJECTORY)
+    gbs2 = 2 * nbytes / (kms2 * 1e-3 / kn2) / 1e9
+    roofline_traj["with_counts"] = {"achieved": gbs2, "unit": "GB/s", "frac": gbs2 / hbm_gbs,
+                                    "frac_of_8TBs_nominal": gbs2 / 8000.0, "algorithmic_bytes": 2 * nbytes,
+                                    "per_unit": "8 B stored per path-step (float price + int barrier count)",
+                                    "kernel_ms": kms2 / kn2, "kernel_launches": kn2}
+    out["trajectories_with_counts_2^20x252"] = {"path_steps_per_s": TRAJ_PATHS * TRAJ_STEPS / t2,
+                                                "GB_per_s": 2 * nbytes / t2 / 1e9, "ms": 1e3 * t2}
+    del buf, cnt
 
     # bullet option, 2^22 paths x 100 steps (hello.cu parameters, r as configs[0])
     ob = pkg.option(N_STEPS=100, N_PATHS=1 << 22, B=120.0, P1=10, P2=50, **CFG)

@@ -671,18 +671,35 @@ static int trajectories_launch(mcb_engine *e, const mcb_option_data *opt, uint64
     const bool vec = (opt->N_STEPS % 4 == 0) && ((uintptr_t)d_prices % 16 == 0) &&
                      (!d_counts || (uintptr_t)d_counts % 16 == 0) && (!d_logs || (uintptr_t)d_logs % 16 == 0);
     cudaStream_t st = pick(e, stream);
-    // prices only, single-pass rows, aligned: the TMA slab kernel (the bandwidth path, config 3)
-    const bool slab = vec && !d_counts && !d_logs && opt->N_STEPS <= pass_steps;
+    // single-pass, aligned rows: the TMA slab kernel (the bandwidth path, config 3); counts and log2
+    // prices ride along in their own staging rows
+    const bool slab = vec && opt->N_STEPS <= pass_steps;
     if (slab) {
-        constexpr int kSlabWarps = 4, kSlabRows = 6;   // tuned on B200 at 2^20 x 252 (profiles/r1_trajectory_tuning.txt)
-        const uint64_t rows_per_cta = (uint64_t)kSlabWarps * kSlabRows;
-        const uint64_t ctas = (n_paths + rows_per_cta - 1) / rows_per_cta;
-        const size_t smem = (size_t)kSlabWarps * kSlabRows * (size_t)opt->N_STEPS * sizeof(float);   // <= 24 KB
+        constexpr int kSlabWarps = 4;
         TimedScope timed(e, MCB_KERNEL_TRAJECTORY, st);
-        if (wide)
-            trajectory_slab_kernel<16, 16, kSlabRows, kSlabWarps><<<(unsigned)ctas, kSlabWarps * 32, smem, st>>>(prm, d_prices);
-        else
-            trajectory_slab_kernel<4, 32, kSlabRows, kSlabWarps><<<(unsigned)ctas, kSlabWarps * 32, smem, st>>>(prm, d_prices);
+        // rows per slab: 6 for one output array (tuned on B200 at 2^20 x 252, profiles/r1_trajectory_tuning.txt),
+        // fewer when counts / logs need their own staging rows
+#define MCB_SLAB(SPL, LPR, ROWS, CNT, LOG)                                                                    \
+    do {                                                                                                      \
+        auto kern = trajectory_slab_kernel<SPL, LPR, ROWS, kSlabWarps, CNT, LOG>;                             \
+        const uint64_t rows_per_cta = (uint64_t)kSlabWarps * ROWS;                                            \
+        const uint64_t ctas = (n_paths + rows_per_cta - 1) / rows_per_cta;                                    \
+        const size_t smem = (size_t)kSlabWarps * (1 + (CNT ? 1 : 0) + (LOG ? 1 : 0)) * ROWS *                 \
+                            (size_t)opt->N_STEPS * sizeof(float);                                             \
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        kern<<<(unsigned)ctas, kSlabWarps * 32, smem, st>>>(prm, d_prices, d_counts, d_logs);                 \
+    } while (0)
+#define MCB_SLAB_ARRAYS(SPL, LPR)                                   \
+    do {                                                            \
+        if (d_counts && d_logs) MCB_SLAB(SPL, LPR, 2, true, true);  \
+        else if (d_counts) MCB_SLAB(SPL, LPR, 4, true, false);      \
+        else if (d_logs) MCB_SLAB(SPL, LPR, 4, false, true);        \
+        else MCB_SLAB(SPL, LPR, 6, false, false);                   \
+    } while (0)
+        if (wide) MCB_SLAB_ARRAYS(16, 16);
+        else MCB_SLAB_ARRAYS(4, 32);
+#undef MCB_SLAB_ARRAYS
+#undef MCB_SLAB
     } else {
         const uint64_t rows_per_cta = (uint64_t)kPathWarps * kPathsPerWarp * (wide ? 2 : 1);
         const uint64_t ctas = (n_paths + rows_per_cta - 1) / rows_per_cta;

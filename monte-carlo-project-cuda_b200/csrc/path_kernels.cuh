@@ -248,8 +248,8 @@ trajectory_kernel(const __grid_constant__ PathParams prm, float *__restrict__ pr
 }
 
 // ------------------------------------------------------------------------------------------
-// Slab kernel (prices only, rows of at most SPL*LPR steps, 16-byte aligned rows): the bandwidth
-// path of BASELINE config 3 (2^20 x 252).
+// Slab kernel (rows of at most SPL*LPR steps, 16-byte aligned rows; optional barrier counts and
+// log2 prices): the bandwidth path of BASELINE config 3 (2^20 x 252).
 // A lane's SPL*4 bytes are whole 32-byte sectors only when the row starts on a sector, and with
 // 1008-byte rows every other row does not; measured (tools/store_probe.cu) a warp storing 32 B
 // per lane reaches 2.9-3.9 TB/s, fully coalesced lines 7.3 TB/s.  So the lanes park their floats
@@ -257,16 +257,18 @@ trajectory_kernel(const __grid_constant__ PathParams prm, float *__restrict__ pr
 // contiguous slab of ROWS*n_steps*4 bytes in the path-major output, one elected lane hands the
 // whole slab to the TMA engine as a single cp.async.bulk (shared::cta -> global): full lines on
 // the L1->L2 crossbar, no per-row address arithmetic, one fence per slab.
-// Dynamic shared memory: kPathWarps * ROWS * n_steps floats.
+// Dynamic shared memory: WARPS * arrays * ROWS * n_steps floats.
 // ------------------------------------------------------------------------------------------
-template <int SPL, int LPR, int ROWS, int WARPS>
+template <int SPL, int LPR, int ROWS, int WARPS, bool COUNTS, bool LOGS>
 __global__ void __launch_bounds__(WARPS * 32)
-trajectory_slab_kernel(const __grid_constant__ PathParams prm, float *__restrict__ prices)
+trajectory_slab_kernel(const __grid_constant__ PathParams prm, float *__restrict__ prices, int *__restrict__ counts,
+                       float *__restrict__ logs)
 {
     constexpr int kBlocks = SPL / 4;
     constexpr int kRowsPerWarp = 32 / LPR;
+    constexpr int kArrays = 1 + (COUNTS ? 1 : 0) + (LOGS ? 1 : 0);
     static_assert(ROWS % kRowsPerWarp == 0, "a slab is a whole number of passes");
-    extern __shared__ __align__(128) float stage[];    // [warp][ROWS][n_steps]
+    extern __shared__ __align__(128) float stage[];    // [warp][array][ROWS][n_steps]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sub = lane / LPR, ln = lane % LPR;
     const int n_steps = prm.n_steps;
@@ -275,7 +277,8 @@ trajectory_slab_kernel(const __grid_constant__ PathParams prm, float *__restrict
     const uint32_t slab_stride = gridDim.x * WARPS;   // a warp strides over the slabs (one each when the grid covers them)
     const int my_step = SPL * ln;
     const bool active = my_step < n_steps;
-    float *my_stage = stage + (size_t)warp * ROWS * n_steps;
+    const int slab_floats = ROWS * n_steps;
+    float *my_stage = stage + (size_t)warp * kArrays * slab_floats;
     float *dst0 = my_stage + sub * n_steps + my_step;
 
 #pragma unroll 1
@@ -291,27 +294,53 @@ trajectory_slab_kernel(const __grid_constant__ PathParams prm, float *__restrict
             float a[SPL];
             const float base = row_finish<SPL, LPR>(prm, words, active, carry_l, a);
 #pragma unroll
-            for (int j = 0; j < SPL; ++j) a[j] = mufu_ex2(base + a[j]);
+            for (int j = 0; j < SPL; ++j) a[j] = base + a[j];          // log2 prices of this lane's steps
+            int cbase = 0;
+            if (COUNTS) {
+                int run = 0;
+#pragma unroll
+                for (int j = 0; j < SPL; ++j) run += (a[j] < prm.lB && my_step + j < n_steps) ? 1 : 0;
+                cbase = group_exclusive_scan<LPR>(run);
+            }
             if (r == 0) {
-                // the previous slab's bulk copy had this whole pass to read the buffer: wait is ~free
+                // the previous slab's bulk copies had this whole pass to read the buffers: wait is ~free
                 if (lane == 0) bulk_wait_read<0>();
                 __syncwarp();
             }
             float *dst = dst0 + r * n_steps;
 #pragma unroll
-            for (int b = 0; b < kBlocks; ++b)
-                if (my_step + 4 * b < n_steps)
-                    *reinterpret_cast<float4 *>(dst + 4 * b) = make_float4(a[4 * b], a[4 * b + 1], a[4 * b + 2], a[4 * b + 3]);
+            for (int b = 0; b < kBlocks; ++b) {
+                if (my_step + 4 * b < n_steps) {
+                    int c[4];
+                    if (COUNTS) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            cbase += (a[4 * b + j] < prm.lB) ? 1 : 0;
+                            c[j] = cbase;
+                        }
+                        *reinterpret_cast<int4 *>(dst + slab_floats + 4 * b) = make_int4(c[0], c[1], c[2], c[3]);
+                    }
+                    if (LOGS)
+                        *reinterpret_cast<float4 *>(dst + (COUNTS ? 2 : 1) * slab_floats + 4 * b) =
+                            make_float4(a[4 * b], a[4 * b + 1], a[4 * b + 2], a[4 * b + 3]);
+                    *reinterpret_cast<float4 *>(dst + 4 * b) = make_float4(mufu_ex2(a[4 * b]), mufu_ex2(a[4 * b + 1]),
+                                                                          mufu_ex2(a[4 * b + 2]), mufu_ex2(a[4 * b + 3]));
+                }
+            }
         }
         fence_async_smem();   // generic-proxy STS -> visible to the async proxy (TMA)
         __syncwarp();
         if (lane == 0) {
             const uint32_t rows = min((uint32_t)ROWS, n_rows - slab_row);
-            bulk_store(prices + (uint64_t)slab_row * (uint32_t)n_steps, my_stage, rows * (uint32_t)n_steps * 4u);
+            const uint32_t bytes = rows * (uint32_t)n_steps * 4u;
+            const uint64_t off = (uint64_t)slab_row * (uint32_t)n_steps;
+            bulk_store(prices + off, my_stage, bytes);
+            if (COUNTS) bulk_store(counts + off, my_stage + slab_floats, bytes);
+            if (LOGS) bulk_store(logs + off, my_stage + (COUNTS ? 2 : 1) * slab_floats, bytes);
             bulk_commit();
         }
     }
-    if (lane == 0) bulk_wait_read<0>();   // shared memory must outlive the last copy's reads
+    if (lane == 0) bulk_wait_read<0>();   // shared memory must outlive the last copies' reads
 }
 
 // ------------------------------------------------------------------------------------------
