@@ -278,6 +278,45 @@ __global__ void curand_blocks_kernel(uint64_t seed, const uint64_t *__restrict__
     out[i] = curand4(&s);
 }
 
+// One row layout (SPL steps per lane, LPR lanes per row): the TMA slab kernel when the row fits one
+// pass and is 16-byte aligned (the bandwidth path, config 3; counts and log2 prices ride along in
+// their own staging rows), the general kernel otherwise.
+template <int SPL, int LPR>
+void launch_trajectory(const PathParams &prm, uint64_t n_paths, bool vec, float *d_prices, int *d_counts,
+                              float *d_logs, cudaStream_t st)
+{
+    constexpr int kRowsPerWarp = 32 / LPR;
+    if (vec && prm.n_steps <= SPL * LPR) {
+        constexpr int kSlabWarps = 4;
+        // rows per slab: ~6 for one output array (tuned on B200 at 2^20 x 252, profiles/r1_trajectory_tuning.txt),
+        // fewer when counts / logs need their own staging rows; always a whole number of passes
+        constexpr int kRows1 = (6 + kRowsPerWarp - 1) / kRowsPerWarp * kRowsPerWarp;
+        constexpr int kRows2 = (4 + kRowsPerWarp - 1) / kRowsPerWarp * kRowsPerWarp;
+        constexpr int kRows3 = (2 + kRowsPerWarp - 1) / kRowsPerWarp * kRowsPerWarp;
+#define MCB_SLAB(ROWS, CNT, LOG)                                                                              \
+    do {                                                                                                      \
+        auto kern = trajectory_slab_kernel<SPL, LPR, ROWS, kSlabWarps, CNT, LOG>;                             \
+        const uint64_t rows_per_cta = (uint64_t)kSlabWarps * ROWS;                                            \
+        const uint64_t ctas = (n_paths + rows_per_cta - 1) / rows_per_cta;                                    \
+        const size_t smem = (size_t)kSlabWarps * (1 + (CNT ? 1 : 0) + (LOG ? 1 : 0)) * ROWS *                 \
+                            (size_t)prm.n_steps * sizeof(float);                                              \
+        kern<<<(unsigned)ctas, kSlabWarps * 32, smem, st>>>(prm, d_prices, d_counts, d_logs);                 \
+    } while (0)
+        if (d_counts && d_logs) MCB_SLAB(kRows3, true, true);
+        else if (d_counts) MCB_SLAB(kRows2, true, false);
+        else if (d_logs) MCB_SLAB(kRows2, false, true);
+        else MCB_SLAB(kRows1, false, false);
+#undef MCB_SLAB
+    } else {
+        const uint64_t rows_per_cta = (uint64_t)kPathWarps * kPathsPerWarp * kRowsPerWarp;
+        const unsigned g = (unsigned)((n_paths + rows_per_cta - 1) / rows_per_cta), b = kPathWarps * 32;
+        if (vec && d_counts) trajectory_kernel<SPL, LPR, kStoreVec4, true><<<g, b, 0, st>>>(prm, d_prices, d_counts, d_logs);
+        else if (vec) trajectory_kernel<SPL, LPR, kStoreVec4, false><<<g, b, 0, st>>>(prm, d_prices, d_counts, d_logs);
+        else if (d_counts) trajectory_kernel<SPL, LPR, kStoreScalar, true><<<g, b, 0, st>>>(prm, d_prices, d_counts, d_logs);
+        else trajectory_kernel<SPL, LPR, kStoreScalar, false><<<g, b, 0, st>>>(prm, d_prices, d_counts, d_logs);
+    }
+}
+
 }  // namespace
 
 // ============================================================================================
@@ -662,65 +701,21 @@ static int trajectories_launch(mcb_engine *e, const mcb_option_data *opt, uint64
     prm.first_path = first_path;
     prm.n_paths = n_paths;
     prm.keys = make_philox_keys(seed);
-    // Row layout, a function of n_steps ONLY (so a row's bits never depend on which arrays were
-    // asked for or which kernel wrote it): rows of <= 128 steps use 32 lanes x 4 steps, longer
-    // rows 16 lanes x 16 steps (two rows side by side per warp).
-    const bool wide = opt->N_STEPS > 128;
-    const int pass_steps = wide ? 256 : 128;
     if (n_paths > 0x7fffffffull) return fail(MCB_ERR_INVALID, "too many paths for one launch");
     const bool vec = (opt->N_STEPS % 4 == 0) && ((uintptr_t)d_prices % 16 == 0) &&
                      (!d_counts || (uintptr_t)d_counts % 16 == 0) && (!d_logs || (uintptr_t)d_logs % 16 == 0);
     cudaStream_t st = pick(e, stream);
-    // single-pass, aligned rows: the TMA slab kernel (the bandwidth path, config 3); counts and log2
-    // prices ride along in their own staging rows
-    const bool slab = vec && opt->N_STEPS <= pass_steps;
-    if (slab) {
-        constexpr int kSlabWarps = 4;
+    {
         TimedScope timed(e, MCB_KERNEL_TRAJECTORY, st);
-        // rows per slab: 6 for one output array (tuned on B200 at 2^20 x 252, profiles/r1_trajectory_tuning.txt),
-        // fewer when counts / logs need their own staging rows
-#define MCB_SLAB(SPL, LPR, ROWS, CNT, LOG)                                                                    \
-    do {                                                                                                      \
-        auto kern = trajectory_slab_kernel<SPL, LPR, ROWS, kSlabWarps, CNT, LOG>;                             \
-        const uint64_t rows_per_cta = (uint64_t)kSlabWarps * ROWS;                                            \
-        const uint64_t ctas = (n_paths + rows_per_cta - 1) / rows_per_cta;                                    \
-        const size_t smem = (size_t)kSlabWarps * (1 + (CNT ? 1 : 0) + (LOG ? 1 : 0)) * ROWS *                 \
-                            (size_t)opt->N_STEPS * sizeof(float);                                             \
-        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        kern<<<(unsigned)ctas, kSlabWarps * 32, smem, st>>>(prm, d_prices, d_counts, d_logs);                 \
-    } while (0)
-#define MCB_SLAB_ARRAYS(SPL, LPR)                                   \
-    do {                                                            \
-        if (d_counts && d_logs) MCB_SLAB(SPL, LPR, 2, true, true);  \
-        else if (d_counts) MCB_SLAB(SPL, LPR, 4, true, false);      \
-        else if (d_logs) MCB_SLAB(SPL, LPR, 4, false, true);        \
-        else MCB_SLAB(SPL, LPR, 6, false, false);                   \
-    } while (0)
-        if (wide) MCB_SLAB_ARRAYS(16, 16);
-        else MCB_SLAB_ARRAYS(4, 32);
-#undef MCB_SLAB_ARRAYS
-#undef MCB_SLAB
-    } else {
-        const uint64_t rows_per_cta = (uint64_t)kPathWarps * kPathsPerWarp * (wide ? 2 : 1);
-        const uint64_t ctas = (n_paths + rows_per_cta - 1) / rows_per_cta;
-        TimedScope timed(e, MCB_KERNEL_TRAJECTORY, st);
-        const unsigned g = (unsigned)ctas, b = kPathWarps * 32;
-#define MCB_TRAJ(SPL, LPR, STORE, CNT) \
-    trajectory_kernel<SPL, LPR, STORE, CNT><<<g, b, 0, st>>>(prm, d_prices, d_counts, d_logs)
-#define MCB_TRAJ_STORES(SPL, LPR)                                     \
-    do {                                                              \
-        if (vec) {                                                    \
-            if (d_counts) MCB_TRAJ(SPL, LPR, kStoreVec4, true);       \
-            else MCB_TRAJ(SPL, LPR, kStoreVec4, false);               \
-        } else {                                                      \
-            if (d_counts) MCB_TRAJ(SPL, LPR, kStoreScalar, true);     \
-            else MCB_TRAJ(SPL, LPR, kStoreScalar, false);             \
-        }                                                             \
-    } while (0)
-        if (wide) MCB_TRAJ_STORES(16, 16);
-        else MCB_TRAJ_STORES(4, 32);
-#undef MCB_TRAJ_STORES
-#undef MCB_TRAJ
+        // Row layout (steps per lane x lanes per row), a function of n_steps ONLY so that a row's
+        // bits never depend on which arrays were asked for or which kernel wrote it: the smallest
+        // pass that holds the whole row, 16 x 16 (several passes) beyond 256 steps.
+        const int n = opt->N_STEPS;
+        if (n <= 32) launch_trajectory<4, 8>(prm, n_paths, vec, d_prices, d_counts, d_logs, st);
+        else if (n <= 64) launch_trajectory<4, 16>(prm, n_paths, vec, d_prices, d_counts, d_logs, st);
+        else if (n <= 128) launch_trajectory<8, 16>(prm, n_paths, vec, d_prices, d_counts, d_logs, st);
+        else if (n <= 192) launch_trajectory<12, 16>(prm, n_paths, vec, d_prices, d_counts, d_logs, st);
+        else launch_trajectory<16, 16>(prm, n_paths, vec, d_prices, d_counts, d_logs, st);
     }
     e->launches++;
     CU(cudaGetLastError());
