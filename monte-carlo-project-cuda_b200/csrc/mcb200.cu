@@ -286,26 +286,39 @@ void launch_trajectory(const PathParams &prm, uint64_t n_paths, bool vec, float 
                               float *d_logs, cudaStream_t st)
 {
     constexpr int kRowsPerWarp = 32 / LPR;
-    if (vec && prm.n_steps <= SPL * LPR) {
-        constexpr int kSlabWarps = 4;
+    constexpr int kSlabWarps = 4;
+    // rows longer than one pass: one row group per slab, the whole rows staged -- while the staging
+    // leaves enough CTAs per SM (measured on 2^20 rows: prices only 4.07 TB/s at 1024 steps / 32 KB,
+    // 3.67 at 1536 / 48 KB, then the general kernel's 3.5 TB/s wins; with counts the general
+    // kernel's direct stores are slow enough that staging pays up to 72 KB); longer or unaligned
+    // rows take the general kernel
+    const int n_arrays = 1 + (d_counts ? 1 : 0) + (d_logs ? 1 : 0);
+    const size_t multi_smem = (size_t)kSlabWarps * n_arrays * kRowsPerWarp * (size_t)prm.n_steps * sizeof(float);
+#define MCB_SLAB(ROWS, CNT, LOG, MULTI)                                                                       \
+    do {                                                                                                      \
+        auto kern = trajectory_slab_kernel<SPL, LPR, ROWS, kSlabWarps, CNT, LOG, MULTI>;                      \
+        const uint64_t rows_per_cta = (uint64_t)kSlabWarps * ROWS;                                            \
+        const uint64_t ctas = (n_paths + rows_per_cta - 1) / rows_per_cta;                                    \
+        const size_t smem = (size_t)kSlabWarps * (1 + (CNT ? 1 : 0) + (LOG ? 1 : 0)) * ROWS *                 \
+                            (size_t)prm.n_steps * sizeof(float);                                              \
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        kern<<<(unsigned)ctas, kSlabWarps * 32, smem, st>>>(prm, d_prices, d_counts, d_logs);                 \
+    } while (0)
+    if (vec && prm.n_steps > SPL * LPR && multi_smem <= (n_arrays == 1 ? 48 : 72) * 1024) {
+        if (d_counts && d_logs) MCB_SLAB(kRowsPerWarp, true, true, true);
+        else if (d_counts) MCB_SLAB(kRowsPerWarp, true, false, true);
+        else if (d_logs) MCB_SLAB(kRowsPerWarp, false, true, true);
+        else MCB_SLAB(kRowsPerWarp, false, false, true);
+    } else if (vec && prm.n_steps <= SPL * LPR) {
         // rows per slab: ~6 for one output array (tuned on B200 at 2^20 x 252, profiles/r1_trajectory_tuning.txt),
         // fewer when counts / logs need their own staging rows; always a whole number of passes
         constexpr int kRows1 = (6 + kRowsPerWarp - 1) / kRowsPerWarp * kRowsPerWarp;
         constexpr int kRows2 = (4 + kRowsPerWarp - 1) / kRowsPerWarp * kRowsPerWarp;
         constexpr int kRows3 = (2 + kRowsPerWarp - 1) / kRowsPerWarp * kRowsPerWarp;
-#define MCB_SLAB(ROWS, CNT, LOG)                                                                              \
-    do {                                                                                                      \
-        auto kern = trajectory_slab_kernel<SPL, LPR, ROWS, kSlabWarps, CNT, LOG>;                             \
-        const uint64_t rows_per_cta = (uint64_t)kSlabWarps * ROWS;                                            \
-        const uint64_t ctas = (n_paths + rows_per_cta - 1) / rows_per_cta;                                    \
-        const size_t smem = (size_t)kSlabWarps * (1 + (CNT ? 1 : 0) + (LOG ? 1 : 0)) * ROWS *                 \
-                            (size_t)prm.n_steps * sizeof(float);                                              \
-        kern<<<(unsigned)ctas, kSlabWarps * 32, smem, st>>>(prm, d_prices, d_counts, d_logs);                 \
-    } while (0)
-        if (d_counts && d_logs) MCB_SLAB(kRows3, true, true);
-        else if (d_counts) MCB_SLAB(kRows2, true, false);
-        else if (d_logs) MCB_SLAB(kRows2, false, true);
-        else MCB_SLAB(kRows1, false, false);
+        if (d_counts && d_logs) MCB_SLAB(kRows3, true, true, false);
+        else if (d_counts) MCB_SLAB(kRows2, true, false, false);
+        else if (d_logs) MCB_SLAB(kRows2, false, true, false);
+        else MCB_SLAB(kRows1, false, false, false);
 #undef MCB_SLAB
     } else {
         const uint64_t rows_per_cta = (uint64_t)kPathWarps * kPathsPerWarp * kRowsPerWarp;

@@ -259,7 +259,7 @@ trajectory_kernel(const __grid_constant__ PathParams prm, float *__restrict__ pr
 // the L1->L2 crossbar, no per-row address arithmetic, one fence per slab.
 // Dynamic shared memory: WARPS * arrays * ROWS * n_steps floats.
 // ------------------------------------------------------------------------------------------
-template <int SPL, int LPR, int ROWS, int WARPS, bool COUNTS, bool LOGS>
+template <int SPL, int LPR, int ROWS, int WARPS, bool COUNTS, bool LOGS, bool MULTI = false>
 __global__ void __launch_bounds__(WARPS * 32)
 trajectory_slab_kernel(const __grid_constant__ PathParams prm, float *__restrict__ prices, int *__restrict__ counts,
                        float *__restrict__ logs)
@@ -275,11 +275,10 @@ trajectory_slab_kernel(const __grid_constant__ PathParams prm, float *__restrict
     const uint32_t n_rows = (uint32_t)prm.n_paths;
     const uint32_t n_slabs = (n_rows + ROWS - 1) / ROWS;
     const uint32_t slab_stride = gridDim.x * WARPS;   // a warp strides over the slabs (one each when the grid covers them)
-    const int my_step = SPL * ln;
-    const bool active = my_step < n_steps;
+    const int lane_step = SPL * ln;
     const int slab_floats = ROWS * n_steps;
     float *my_stage = stage + (size_t)warp * kArrays * slab_floats;
-    float *dst0 = my_stage + sub * n_steps + my_step;
+    float *dst0 = my_stage + sub * n_steps + lane_step;
 
 #pragma unroll 1
     for (uint32_t slab = blockIdx.x * WARPS + warp; slab < n_slabs; slab += slab_stride) {
@@ -289,42 +288,52 @@ trajectory_slab_kernel(const __grid_constant__ PathParams prm, float *__restrict
 #pragma unroll 1
         for (int r = 0; r < ROWS; r += kRowsPerWarp) {
             const uint64_t p = prm.first_path + slab_row + (uint32_t)(r + sub);   // rows past n_rows: computed, not copied
-            const PassWords<SPL> words = row_words<SPL>(prm, (uint32_t)p, (uint32_t)(p >> 32), my_step);
             float carry_l = prm.l0;
-            float a[SPL];
-            const float base = row_finish<SPL, LPR>(prm, words, active, carry_l, a);
+            int carry_c = 0;
+            // MULTI: rows longer than one pass (SPL*LPR steps) take several, the running log2 price
+            // and barrier count carried in registers; otherwise exactly one trip
+#pragma unroll 1
+            for (int step0 = 0; step0 < (MULTI ? n_steps : 1); step0 += SPL * LPR) {
+                const int my_step = step0 + lane_step;
+                const bool active = my_step < n_steps;
+                const PassWords<SPL> words = row_words<SPL>(prm, (uint32_t)p, (uint32_t)(p >> 32), my_step);
+                float a[SPL];
+                const float base = row_finish<SPL, LPR>(prm, words, active, carry_l, a);
 #pragma unroll
-            for (int j = 0; j < SPL; ++j) a[j] = base + a[j];          // log2 prices of this lane's steps
-            int cbase = 0;
-            if (COUNTS) {
-                int run = 0;
+                for (int j = 0; j < SPL; ++j) a[j] = base + a[j];          // log2 prices of this lane's steps
+                int cbase = carry_c;
+                if (COUNTS) {
+                    int run = 0;
 #pragma unroll
-                for (int j = 0; j < SPL; ++j) run += (a[j] < prm.lB && my_step + j < n_steps) ? 1 : 0;
-                cbase = group_exclusive_scan<LPR>(run);
-            }
-            if (r == 0) {
-                // the previous slab's bulk copies had this whole pass to read the buffers: wait is ~free
-                if (lane == 0) bulk_wait_read<0>();
-                __syncwarp();
-            }
-            float *dst = dst0 + r * n_steps;
+                    for (int j = 0; j < SPL; ++j) run += (a[j] < prm.lB && my_step + j < n_steps) ? 1 : 0;
+                    cbase += group_exclusive_scan<LPR>(run);
+                    if (MULTI) carry_c = __shfl_sync(kFullMask, cbase + run, LPR - 1, LPR);
+                }
+                if (r == 0 && step0 == 0) {
+                    // the previous slab's bulk copies had this whole pass to read the buffers: wait is ~free
+                    if (lane == 0) bulk_wait_read<0>();
+                    __syncwarp();
+                }
+                float *dst = dst0 + r * n_steps + step0;
 #pragma unroll
-            for (int b = 0; b < kBlocks; ++b) {
-                if (my_step + 4 * b < n_steps) {
-                    int c[4];
-                    if (COUNTS) {
+                for (int b = 0; b < kBlocks; ++b) {
+                    if (my_step + 4 * b < n_steps) {
+                        int c[4];
+                        if (COUNTS) {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            cbase += (a[4 * b + j] < prm.lB) ? 1 : 0;
-                            c[j] = cbase;
+                            for (int j = 0; j < 4; ++j) {
+                                cbase += (a[4 * b + j] < prm.lB) ? 1 : 0;
+                                c[j] = cbase;
+                            }
+                            *reinterpret_cast<int4 *>(dst + slab_floats + 4 * b) = make_int4(c[0], c[1], c[2], c[3]);
                         }
-                        *reinterpret_cast<int4 *>(dst + slab_floats + 4 * b) = make_int4(c[0], c[1], c[2], c[3]);
+                        if (LOGS)
+                            *reinterpret_cast<float4 *>(dst + (COUNTS ? 2 : 1) * slab_floats + 4 * b) =
+                                make_float4(a[4 * b], a[4 * b + 1], a[4 * b + 2], a[4 * b + 3]);
+                        *reinterpret_cast<float4 *>(dst + 4 * b) =
+                            make_float4(mufu_ex2(a[4 * b]), mufu_ex2(a[4 * b + 1]), mufu_ex2(a[4 * b + 2]),
+                                        mufu_ex2(a[4 * b + 3]));
                     }
-                    if (LOGS)
-                        *reinterpret_cast<float4 *>(dst + (COUNTS ? 2 : 1) * slab_floats + 4 * b) =
-                            make_float4(a[4 * b], a[4 * b + 1], a[4 * b + 2], a[4 * b + 3]);
-                    *reinterpret_cast<float4 *>(dst + 4 * b) = make_float4(mufu_ex2(a[4 * b]), mufu_ex2(a[4 * b + 1]),
-                                                                          mufu_ex2(a[4 * b + 2]), mufu_ex2(a[4 * b + 3]));
                 }
             }
         }
