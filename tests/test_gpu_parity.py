@@ -320,7 +320,8 @@ def test_bullet_without_barrier_is_european(engine, orc, pkg):
 
 # -------------------------------------------------------------------------------- trajectories
 @pytest.mark.parametrize("n_steps,n_paths,first", [(252, 300, 0), (100, 129, 1000), (7, 33, 5), (1, 64, 0),
-                                                   (33, 31, (1 << 32) - 16), (64, 1, 9)])
+                                                   (33, 31, (1 << 32) - 16), (64, 1, 9), (32, 40, 0), (150, 20, 0),
+                                                   (192, 9, 7), (300, 9, 0), (600, 5, 3), (1023, 3, 1), (5000, 2, 0)])
 def test_trajectories_vs_oracle(engine, orc, pkg, n_steps, n_paths, first):
     """Path-major prices[p][i] = S(t_{i+1}) and barrier counts.  FP32 log2-space accumulation over
     n_steps steps: relative error <= ~n_steps * 2^-24 * |log2 S| ~ 1e-4 at 252 steps -> rtol 3e-4.
