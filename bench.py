@@ -264,7 +264,7 @@ def run_b200(args):
     import importlib
     sharded = importlib.import_module(entry.PKG_NAME + ".sharded")
     eng = pkg.Engine(local)
-    pricer = sharded.ShardedPricer(eng)
+    pricer = sharded.ShardedPricer(eng, transport=args.transport)
     hbm_gbs, sm_max_mhz, peak_src = measured_peaks()
 
     strong = args.scaling == "strong"
@@ -339,7 +339,9 @@ def run_b200(args):
         "config": {"workload": f"European call S0=100 K=100 r=0.05 sigma=0.2 T=1, single step, "
                                f"{'2^30 paths in total' if strong else '2^30 paths per GPU'} "
                                f"({n_total} paths total), seed {SEED}, Philox4x32-10 keyed by (seed, path id)",
-                   "paths_per_gpu": n_total // world, "parallelism": f"path-index shards x{world}, one allreduce of 1 KiB",
+                   "paths_per_gpu": n_total // world,
+                   "parallelism": f"path-index shards x{world}, " + ("one NCCL allreduce of 1 KiB" if args.transport == "nccl"
+                                                                      else "segments all-gathered by NVLink peer stores"),
                    "l2": "n/a: the kernel reads no global memory (64 Ki chunk partials of 8 B written per launch)",
                    **CFG},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -523,6 +525,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak (default): 2^30 paths per GPU; strong: 2^30 paths in total")
+    ap.add_argument("--transport", default="nccl", choices=["nccl", "peer"],
+                    help="N > 1: how the 64 partial-sum segments cross GPUs: one NCCL all-reduce (default) or direct "
+                         "NVLink stores into CUDA-IPC peer mailboxes from inside the segment pass")
     ap.add_argument("--headline-only", action="store_true", help="skip the other BASELINE configs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

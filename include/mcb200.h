@@ -182,6 +182,27 @@ int mcb_nested_async(mcb_engine *e, const mcb_option_data *opt, uint64_t first_o
                      uint64_t seed_outer, uint64_t seed_inner, int discount_mode, float *d_F,
                      float *d_prices, int *d_counts, void *stream);
 
+/* ---- NCCL-free exchange over NVLink peer memory (optional; no reference counterpart) --------
+ * The only data that crosses GPUs is the 64 (sum, sumsq) segments (1 KiB).  Instead of handing
+ * them to a collective library, the segment pass of rank g can STORE the segments it owns straight
+ * into every peer's mailbox (st.global on CUDA-IPC-mapped peer memory, NVLink / NVSwitch), publish
+ * an epoch flag, and the final pass of every rank waits (bounded spin on its OWN memory) for the G
+ * flags before running the fixed tree: compute + all-gather in two launches, bit-identical to the
+ * single-GPU result.  One process per GPU:
+ *   mcb_peer_mailbox_create   allocates this rank's mailbox, returns its 64-byte cudaIpcMemHandle;
+ *   (the caller all-gathers the handles, e.g. torch.distributed.all_gather_object)
+ *   mcb_peer_mailbox_connect  maps every peer's mailbox;
+ *   mcb_european_peer_async   european chunks -> peer-storing segment pass -> waiting final pass,
+ *                             all enqueued on `stream`; d_results receives one mcb_result.
+ * Every rank must issue the same sequence of *_peer_async calls.  The wait is bounded (~seconds):
+ * on timeout the result's n_paths is set to 0 instead of hanging. */
+#define MCB_IPC_HANDLE_BYTES 64
+#define MCB_MAX_PEERS 16
+int mcb_peer_mailbox_create(mcb_engine *e, void *handle_out);
+int mcb_peer_mailbox_connect(mcb_engine *e, int rank, int world, const void *all_handles);
+int mcb_european_peer_async(mcb_engine *e, const mcb_option_data *opt, uint64_t n_paths, uint64_t seed,
+                            int option_type, mcb_result *d_results, void *stream);
+
 /* Number of kernel launches this engine has issued (bench.py's gpu_launches). */
 uint64_t mcb_launch_count(mcb_engine *e);
 

@@ -113,6 +113,9 @@ SIGNATURES = {
     "mcb_combine_segments_async": (C.c_int, [_vp, _vp, C.c_int, _u64, C.c_float, C.c_float, _vp, _vp]),
     "mcb_trajectories_async": (C.c_int, [_vp, _OP, _u64, _u64, _u64, _vp, _vp, _vp]),
     "mcb_nested_async": (C.c_int, [_vp, _OP, _u64, _u64, _u64, _u64, C.c_int, _vp, _vp, _vp, _vp]),
+    "mcb_peer_mailbox_create": (C.c_int, [_vp, _vp]),
+    "mcb_peer_mailbox_connect": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
+    "mcb_european_peer_async": (C.c_int, [_vp, _OP, _u64, _u64, C.c_int, _vp, _vp]),
     "mcb_launch_count": (_u64, [_vp]),
     "mcb_timing_enable": (C.c_int, [_vp, C.c_int]),
     "mcb_timing_read": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_double), C.POINTER(_u64)]),
@@ -299,6 +302,21 @@ class Engine:
 
     def combine_segments_async(self, d_segments, n_sets, n_paths, r, T, d_results, stream=None):
         _check(self._lib.mcb_combine_segments_async(self._h, d_segments, n_sets, n_paths, r, T, d_results, stream))
+
+    # ---- NCCL-free exchange over NVLink peer memory ------------------------------------------------
+    def peer_mailbox_create(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        _check(self._lib.mcb_peer_mailbox_create(self._h, buf))
+        return buf.raw
+
+    def peer_mailbox_connect(self, rank, world, handles):
+        blob = b"".join(handles)
+        if len(blob) != 64 * world:
+            raise ValueError("need one 64-byte handle per rank")
+        _check(self._lib.mcb_peer_mailbox_connect(self._h, rank, world, blob))
+
+    def european_peer_async(self, opt, n_paths, seed, option_type, d_results, stream=None):
+        _check(self._lib.mcb_european_peer_async(self._h, C.byref(opt), n_paths, seed, option_type, d_results, stream))
 
     # ---- parity hooks ------------------------------------------------------------------------
     def philox_blocks(self, seed, subsequences, blocks, library=False):

@@ -91,6 +91,12 @@ struct mcb_engine {
     DeviceBuffer<float> nested_ws;         // nested MC: log2 S, (prices), (counts) of the outer points
     DeviceBuffer<float4> sweep_sets;       // sweep: (c0, c1, K, -) per parameter set
     std::vector<float4> h_sweep_sets;      // host staging for sweep_sets (pageable on purpose)
+    // peer-memory exchange (mcb_peer_mailbox_*): my mailbox, the peers' mailboxes mapped over CUDA IPC
+    PeerMailbox *mailbox = nullptr;
+    PeerTable peers{};
+    void *peer_mapped[kMaxPeers] = {};     // what cudaIpcOpenMemHandle returned (to close on destroy)
+    int peer_rank = -1, peer_world = 0;
+    unsigned long long peer_epoch = 0;
     mcb_result *h_results = nullptr;       // pinned
     size_t h_results_cap = 0;
     double *h_segments = nullptr;          // pinned, [MCB_SEGMENTS][2] of the last whole-job call
@@ -400,6 +406,9 @@ int mcb_engine_destroy(mcb_engine *e)
     e->scratch.release();
     e->nested_ws.release();
     e->sweep_sets.release();
+    for (int r = 0; r < kMaxPeers; ++r)
+        if (e->peer_mapped[r]) cudaIpcCloseMemHandle(e->peer_mapped[r]);
+    if (e->mailbox) cudaFree(e->mailbox);
     if (e->h_results) cudaFreeHost(e->h_results);
     if (e->h_segments) cudaFreeHost(e->h_segments);
     delete e;
@@ -426,6 +435,87 @@ int mcb_synchronize(mcb_engine *e)
     if (!e) return fail(MCB_ERR_INVALID, "engine is NULL");
     DeviceGuard g(e->device);
     CU(cudaStreamSynchronize(e->stream));
+    return MCB_OK;
+}
+
+// --------------------------------------------------------------- peer-memory exchange (NVLink)
+static_assert(MCB_MAX_PEERS == kMaxPeers && MCB_IPC_HANDLE_BYTES == sizeof(cudaIpcMemHandle_t), "peer ABI");
+
+int mcb_peer_mailbox_create(mcb_engine *e, void *handle_out)
+{
+    if (!e || !handle_out) return fail(MCB_ERR_INVALID, "NULL argument");
+    DeviceGuard g(e->device);
+    if (!e->mailbox) {
+        CU(cudaMalloc(&e->mailbox, sizeof(PeerMailbox)));
+        CU(cudaMemset(e->mailbox, 0, sizeof(PeerMailbox)));
+    }
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, e->mailbox));
+    memcpy(handle_out, &h, sizeof(h));
+    return MCB_OK;
+}
+
+int mcb_peer_mailbox_connect(mcb_engine *e, int rank, int world, const void *all_handles)
+{
+    if (!e || !all_handles) return fail(MCB_ERR_INVALID, "NULL argument");
+    if (!e->mailbox) return fail(MCB_ERR_INVALID, "call mcb_peer_mailbox_create first");
+    if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world)
+        return fail(MCB_ERR_INVALID, "bad rank/world %d/%d (at most %d peers)", rank, world, kMaxPeers);
+    if (MCB_SEGMENTS % world != 0) return fail(MCB_ERR_INVALID, "world must divide %d", MCB_SEGMENTS);
+    DeviceGuard g(e->device);
+    const cudaIpcMemHandle_t *h = static_cast<const cudaIpcMemHandle_t *>(all_handles);
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) {
+            e->peers.box[r] = e->mailbox;
+            continue;
+        }
+        if (e->peer_mapped[r]) {
+            cudaIpcCloseMemHandle(e->peer_mapped[r]);
+            e->peer_mapped[r] = nullptr;
+        }
+        void *p = nullptr;
+        CU(cudaIpcOpenMemHandle(&p, h[r], cudaIpcMemLazyEnablePeerAccess));
+        e->peer_mapped[r] = p;
+        e->peers.box[r] = static_cast<PeerMailbox *>(p);
+    }
+    e->peer_rank = rank;
+    e->peer_world = world;
+    e->peer_epoch = 0;
+    return MCB_OK;
+}
+
+int mcb_european_peer_async(mcb_engine *e, const mcb_option_data *opt, uint64_t n_paths, uint64_t seed,
+                            int option_type, mcb_result *d_results, void *stream)
+{
+    int rc = check_common(e, opt);
+    if (rc) return rc;
+    if (e->peer_world < 1) return fail(MCB_ERR_INVALID, "peer mailboxes are not connected");
+    if (!d_results) return fail(MCB_ERR_INVALID, "d_results is NULL");
+    if (option_type != MCB_CALL && option_type != MCB_PUT) return fail(MCB_ERR_INVALID, "bad option_type");
+    n_paths = resolve_paths(opt, n_paths);
+    if (n_paths == 0) return fail(MCB_ERR_INVALID, "n_paths must be > 0");
+    DeviceGuard g(e->device);
+    cudaStream_t st = pick(e, stream);
+    const int rank = e->peer_rank, world = e->peer_world;
+    const uint64_t n_chunks = (n_paths + kEuropeanChunk - 1) / kEuropeanChunk;
+    int seg_lo, seg_hi;
+    uint64_t c_lo, c_hi;
+    segment_span(rank, world, n_chunks, &seg_lo, &seg_hi, &c_lo, &c_hi);
+    if ((rc = e->partials.reserve((size_t)(c_hi - c_lo) + 1))) return rc;
+    const EuropeanParams prm = european_params(opt, opt->K, opt->v, n_paths, seed, c_lo);
+    if ((rc = launch_european<MCB_EUROPEAN_PATHS_PER_SLOT>(e, prm, option_type, c_hi - c_lo, e->partials.ptr, nullptr,
+                                                           0, st)))
+        return rc;
+    const unsigned long long epoch = ++e->peer_epoch;
+    segment_peer_kernel<<<(unsigned)(seg_hi - seg_lo), kSlots, 0, st>>>(e->partials.ptr, c_lo, n_chunks, seg_lo, seg_hi,
+                                                                        e->peers, rank, world, epoch);
+    e->launches++;
+    CU(cudaGetLastError());
+    const double discount = std::exp(-(double)opt->r * (double)opt->T);
+    combine_peer_kernel<<<1, 32, 0, st>>>(e->mailbox, world, epoch, n_paths, discount,
+                                          reinterpret_cast<ResultDev *>(d_results));
+    e->launches++;
+    CU(cudaGetLastError());
     return MCB_OK;
 }
 

@@ -369,6 +369,54 @@ segment_kernel(const float2 *__restrict__ partials, uint64_t partials_stride, ui
     }
 }
 
+// ---- peer-memory exchange (see include/mcb200.h, "NCCL-free exchange") ------------------------
+constexpr int kMaxPeers = 16;  // MCB_MAX_PEERS
+struct PeerMailbox {           // one per rank, in that rank's HBM, written by every peer over NVLink
+    double gather[2][kSegments * 2];            // parity-buffered (sum, sumsq) segments
+    unsigned long long flags[2][kMaxPeers];     // flags[parity][r] = last epoch rank r has published
+    unsigned int ticket;                        // local: CTAs of the segment pass that have finished
+};
+struct PeerTable {
+    PeerMailbox *box[kMaxPeers];                // box[r] = rank r's mailbox as mapped into this process
+};
+
+// Segment pass that all-gathers by peer stores: CTA s folds segment s exactly like segment_kernel
+// when this rank owns it and writes the pair into EVERY rank's mailbox; the last owning CTA to
+// finish publishes this rank's epoch flag everywhere.
+__global__ void __launch_bounds__(kSlots)
+segment_peer_kernel(const float2 *__restrict__ partials, uint64_t partials_first_chunk, uint64_t n_chunks, int seg_lo,
+                    int seg_hi, PeerTable peers, int rank, int world, unsigned long long epoch)
+{
+    __shared__ double scratch[2 * kWarps];
+    const int seg = seg_lo + blockIdx.x;       // grid = owned segments only
+    const int parity = (int)(epoch & 1ull);
+    double a = 0.0, b = 0.0;
+    const uint64_t lo = (n_chunks * (uint64_t)seg) / kSegments;
+    const uint64_t hi = (n_chunks * (uint64_t)(seg + 1)) / kSegments;
+    for (uint64_t c = lo + threadIdx.x; c < hi; c += kSlots) {
+        const float2 v = partials[c - partials_first_chunk];
+        a = a + (double)v.x;
+        b = b + (double)v.y;
+    }
+    block_fold2(a, b, scratch);
+    if (threadIdx.x == 0) {
+        for (int r = 0; r < world; ++r) {
+            double *dst = peers.box[r]->gather[parity] + 2 * seg;
+            __stcg(dst, a);
+            __stcg(dst + 1, b);
+        }
+        __threadfence_system();                 // my segment is visible everywhere before I take a ticket
+        PeerMailbox *mine = peers.box[rank];
+        const unsigned int owned = (unsigned int)(seg_hi - seg_lo);
+        if (atomicAdd(&mine->ticket, 1u) == owned - 1u) {
+            mine->ticket = 0u;                  // ready for the next call (stream-ordered)
+            __threadfence_system();
+            for (int r = 0; r < world; ++r)
+                *((volatile unsigned long long *)&peers.box[r]->flags[parity][rank]) = epoch;
+        }
+    }
+}
+
 struct ResultDev {  // == mcb_result
     double price, std_error, sum, sumsq;
     uint64_t n_paths;
@@ -396,6 +444,49 @@ combine_kernel(const double *__restrict__ segments, uint64_t n_paths, double dis
         r.sumsq = q;
         r.n_paths = n_paths;
         out[set] = r;
+    }
+}
+
+// Final pass behind segment_peer_kernel: wait (bounded) until every rank has published `epoch` in
+// MY mailbox, then the same fixed tree as combine_kernel.  On timeout n_paths is reported as 0.
+__global__ void __launch_bounds__(32)
+combine_peer_kernel(PeerMailbox *__restrict__ mine, int world, unsigned long long epoch, uint64_t n_paths,
+                    double discount, ResultDev *__restrict__ out)
+{
+    const int lane = threadIdx.x;
+    const int parity = (int)(epoch & 1ull);
+    bool ok = true;
+    if (lane < world) {
+        const volatile unsigned long long *flag = &mine->flags[parity][lane];
+        unsigned int spins = 0;
+        while (*flag < epoch) {
+            if (++spins > (1u << 24)) {         // ~seconds: a peer never arrived
+                ok = false;
+                break;
+            }
+            __nanosleep(100);
+        }
+    }
+    ok = __all_sync(kFullMask, ok);
+    __threadfence_system();
+    const volatile double *seg = mine->gather[parity];
+    double s = seg[2 * lane] + seg[2 * (lane + 32)];
+    double q = seg[2 * lane + 1] + seg[2 * (lane + 32) + 1];
+    s = warp_fold(s);
+    q = warp_fold(q);
+    if (lane == 0) {
+        const double n = (double)n_paths;
+        const double mean = s / n;
+        double var = q / n - mean * mean;
+        var = var > 0.0 ? var : 0.0;
+        if (n_paths > 1) var *= n / (n - 1.0);
+        ResultDev r;
+        r.price = discount * mean;
+        r.std_error = discount * sqrt(var / n);
+        r.sum = s;
+        r.sumsq = q;
+        r.n_paths = ok ? n_paths : 0;
+        out[0] = r;
     }
 }
 
