@@ -370,6 +370,32 @@ def run_b200(args):
             "kernel_share_of_step": kern_ms / kern_n / (ms_total / args.steps),
         }
 
+    # ---- BASELINE configs[4] across the ranks (N > 1): the 1024-set x 2^26-path sweep sharded by path
+    #      index, ONE all-reduce of the 1 MiB segment block, prices bit-identical to the 1-GPU job ----
+    if world > 1 and not args.headline_only:
+        sampler.phase = "extra"
+        import numpy as np
+        K, V = np.meshgrid(np.linspace(60, 140, 32, dtype=np.float32), np.linspace(0.05, 0.8, 32, dtype=np.float32),
+                           indexing="ij")
+        k, v = K.ravel().copy(), V.ravel().copy()
+        nccl_pricer = pricer if args.transport == "nccl" else sharded.ShardedPricer(eng, max_sets=1024)
+        for _ in range(2):
+            nccl_pricer.sweep_async(opt, k, v, 1 << 26, SEED, pkg.CALL)
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 5
+        s0.record()
+        for _ in range(reps):
+            nccl_pricer.sweep_async(opt, k, v, 1 << 26, SEED, pkg.CALL)
+        s1.record()
+        barrier()
+        t_sweep = max_over_ranks(float(s0.elapsed_time(s1))) * 1e-3 / reps
+        res = nccl_pricer._fetch(1024)
+        line["other_workloads"] = {"sweep_1024x2^26_sharded": {
+            "path_params_per_s": 1024 * (1 << 26) / t_sweep, "ms": 1e3 * t_sweep, "scaling": "strong",
+            "collective": "one NCCL all-reduce of 1024 x 64 x 2 doubles (1 MiB)",
+            "price_K100_v0.2ish": res[16 * 32 + 6].price, "bound_per_gpu": "XU: 4.65e12 (path.set)/s"}}
+
     # ---- other configs of BASELINE.json (rank 0, N = 1 only): bounded, each device-timed ----
     if world == 1 and not args.headline_only:
         sampler.phase = "extra"
