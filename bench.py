@@ -255,9 +255,12 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit("no CUDA device: this engine has no CPU fallback")
     torch.cuda.set_device(local)
+    # stdout is reserved for the ONE JSON line: libraries that print there (NCCL's version banner does)
+    # are sent to stderr at the file-descriptor level, the line goes out through the saved descriptor
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        # NCCL prints its version banner on stdout; stdout is reserved for the ONE JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     pkg = entry.load_package()
@@ -431,7 +434,9 @@ def run_b200(args):
             line["reference_gpu_baseline"] = ref_gpu
 
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+    os.close(json_fd)
     eng.close()
     if world > 1:
         dist.destroy_process_group()
