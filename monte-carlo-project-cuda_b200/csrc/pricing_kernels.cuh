@@ -117,7 +117,7 @@ struct SweepParams {
     uint64_t first_chunk;  // chunk index of blockIdx.x == 0
     uint64_t stride;       // float2 elements between consecutive parameter sets in `partials`
     int n_sets;
-    uint32_t pad;
+    int sets_per_cta;      // blockIdx.y walks the sets [y*sets_per_cta, (y+1)*sets_per_cta): more, shorter CTAs
     PhiloxKeys keys;
 };
 
@@ -147,13 +147,17 @@ sweep_kernel(const __grid_constant__ SweepParams prm, const float4 *__restrict__
         unit[i] = unit_normal_sin(w.x, w.y);
     }
 
-    for (int s0 = 0; s0 < prm.n_sets; s0 += kSweepTile) {
+    // splitting the sets over blockIdx.y repeats the draw (57 instructions per path against 7 per
+    // (path, set)) but keeps the grid at many waves when a rank owns few chunks
+    const int set_begin = (int)blockIdx.y * prm.sets_per_cta;
+    const int set_end = min(prm.n_sets, set_begin + prm.sets_per_cta);
+    for (int s0 = set_begin; s0 < set_end; s0 += kSweepTile) {
         float sum[kSweepTile], sq[kSweepTile];
 #pragma unroll
         for (int k = 0; k < kSweepTile; ++k) {
             sum[k] = 0.0f;
             sq[k] = 0.0f;
-            if (s0 + k < prm.n_sets) {
+            if (s0 + k < set_end) {
                 const float4 c = __ldg(sets + s0 + k);
                 if (n_valid == PPS) {
 #pragma unroll
@@ -201,7 +205,7 @@ sweep_kernel(const __grid_constant__ SweepParams prm, const float4 *__restrict__
             if (lane == 0) {
 #pragma unroll
                 for (int k = 0; k < kSweepTile; ++k)
-                    if (s0 + k < prm.n_sets)
+                    if (s0 + k < set_end)
                         partials[(uint64_t)(s0 + k) * prm.stride + blockIdx.x] = make_float2(sum[k], sq[k]);
             }
         }
