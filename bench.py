@@ -506,14 +506,14 @@ def other_workloads(torch, pkg, eng, hbm_gbs, peak_src):
                                                 "GB_per_s": 2 * nbytes / t2 / 1e9, "ms": 1e3 * t2}
     del buf, cnt
 
-    # bullet option, 2^22 paths x 100 steps (hello.cu parameters, r as configs[0])
-    ob = pkg.option(N_STEPS=100, N_PATHS=1 << 22, B=120.0, P1=10, P2=50, **CFG)
+    # bullet option, 2^24 paths x 100 steps (hello.cu parameters, r as configs[0]); 16 384 CTAs = 18 waves
+    ob = pkg.option(N_STEPS=100, N_PATHS=1 << 24, B=120.0, P1=10, P2=50, **CFG)
     seg = torch.zeros(2 * pkg.SEGMENTS, dtype=torch.float64, device="cuda")
-    t = timed(lambda: eng.bullet_segments_async(ob, 1 << 22, SEED, 0, 0.0, 0, 0, 1, seg.data_ptr(), stream), 10)
+    t = timed(lambda: eng.bullet_segments_async(ob, 1 << 24, SEED, 0, 0.0, 0, 0, 1, seg.data_ptr(), stream), 10)
     walk_bound = 148 * 30.0 * 1.965e9 / 4.75   # fmaheavy: ~4.75 IMAD.WIDE per step at ~30 /clk/SM (measured)
-    out["bullet_2^22x100"] = {"path_steps_per_s": (1 << 22) * 100 / t, "ms": 1e3 * t,
+    out["bullet_2^24x100"] = {"path_steps_per_s": (1 << 24) * 100 / t, "ms": 1e3 * t,
                               "bound": "fmaheavy: 4.75 IMAD.WIDE per path-step at 30/clk/SM (measured) = 1.84e12 /s",
-                              "frac": (1 << 22) * 100 / t / walk_bound}
+                              "frac": (1 << 24) * 100 / t / walk_bound}
 
     # configs[3]: nested MC 4096 outer x 4096 inner x 100 steps = 8.30e10 inner path-steps
     on = pkg.option(N_STEPS=100, N_PATHS=4096, N_PATHS_INNER=4096, B=120.0, P1=10, P2=50, **CFG)

@@ -139,3 +139,35 @@ def test_reference_mains_run_on_the_new_engine():
         assert "Testing reduction: 6" in out and "Total size: 3000" in out
         lines = open(os.path.join(d, "testing.csv")).read().splitlines()
         assert lines[0] == "time,trajectory,value" and len(lines) == 1 + 20 * 151
+
+
+def test_c_abi_from_plain_c_builds_and_fails_loudly_without_a_gpu(pkg):
+    """examples/price_c.c: gcc -std=c99 against include/mcb200.h only.  On a box without a B200 the
+    program must report "no engine" and exit 2 -- there is no CPU fallback behind the C-ABI."""
+    import torch
+    import __graft_entry__ as entry
+    entry._load_build_module().build()
+    entry.build_examples()
+    exe = os.path.join(ROOT, "build", "price_c")
+    assert os.access(exe, os.X_OK)
+    if not torch.cuda.is_available():
+        out = subprocess.run([exe], capture_output=True, text=True)
+        assert out.returncode == 2 and "no engine" in out.stderr and "no CPU fallback" in out.stderr
+
+
+@pytest.mark.gpu
+def test_c_abi_from_plain_c_runs(pkg, engine):
+    import __graft_entry__ as entry
+    entry.build_examples()
+    out = subprocess.run([os.path.join(ROOT, "build", "price_c")], capture_output=True, text=True, check=True).stdout
+    vals = [ln for ln in out.splitlines() if ln.startswith("C_ABI")][0].split()[1:]
+    rc, bad_rc = int(vals[0]), int(vals[1])
+    call, se, put, bullet, first, last = map(float, vals[2:])
+    assert rc == 0 and bad_rc == pkg.ERR_INVALID
+    opt = pkg.option(N_PATHS=1 << 20, N_STEPS=100, N_PATHS_INNER=1000, step=0.01)
+    assert call == engine.price_european(opt, 0, 1234, pkg.CALL).price
+    assert put == engine.price_european(opt, 0, 1234, pkg.PUT).price
+    assert bullet == engine.price_bullet(opt, 0, 1234).price
+    rows = engine.simulate_trajectories(opt, 0, 8, 1234)
+    assert np.float32(first) == rows[0, 0] and np.float32(last) == rows[7, 99]
+    assert abs((call - put) - (100.0 - 100.0 * np.exp(-0.05))) < 4 * 20.0 / 1024
