@@ -24,7 +24,7 @@ int main(void)
     mcb_option_data bad = opt;
     bad.S0 = -1.0f;
     const int bad_rc = mcb_price_european(engine, &bad, 0, 1234, MCB_CALL, &call);
-    printf("C_ABI %d %d %.9g %.9g %.9g %.9g %.9g %.9g\n", rc, bad_rc, call.price, call.std_error, put.price, bullet.price,
+    printf("C_ABI %d %d %.17g %.17g %.17g %.17g %.9g %.9g\n", rc, bad_rc, call.price, call.std_error, put.price, bullet.price,
            (double)rows[0], (double)rows[799]);
     printf("parity C - P = %.6f, S0 - K e^{-rT} = %.6f\n", call.price - put.price, 100.0 - 100.0 * exp(-0.05));
     free(rows);
