@@ -89,6 +89,7 @@ struct mcb_engine {
     DeviceBuffer<ResultDev> results;
     DeviceBuffer<unsigned char> scratch;   // hooks / host<->device staging
     DeviceBuffer<float> nested_ws;         // nested MC: log2 S, (prices), (counts) of the outer points
+    DeviceBuffer<float> traj_ws;           // mcb_simulate_trajectories to a host buffer: one slab of rows (+ counts)
     DeviceBuffer<float4> sweep_sets;       // sweep: (c0, c1, K, -) per parameter set
     std::vector<float4> h_sweep_sets;      // host staging for sweep_sets (pageable on purpose)
     // peer-memory exchange (mcb_peer_mailbox_*): my mailbox, the peers' mailboxes mapped over CUDA IPC
@@ -405,6 +406,7 @@ int mcb_engine_destroy(mcb_engine *e)
     e->results.release();
     e->scratch.release();
     e->nested_ws.release();
+    e->traj_ws.release();
     e->sweep_sets.release();
     for (int r = 0; r < kMaxPeers; ++r)
         if (e->peer_mapped[r]) cudaIpcCloseMemHandle(e->peer_mapped[r]);
@@ -855,28 +857,27 @@ int mcb_simulate_trajectories(mcb_engine *e, const mcb_option_data *opt, uint64_
         return MCB_OK;
     }
     if (where != MCB_HOST) return fail(MCB_ERR_INVALID, "bad `where`");
-    const size_t n = (size_t)n_paths * (size_t)opt->N_STEPS;
-    if (n == 0) return MCB_OK;
-    float *dp = nullptr;
-    int *dc = nullptr;
-    cudaError_t err = cudaMalloc(&dp, n * sizeof(float));
-    if (err == cudaSuccess && counts) err = cudaMalloc(&dc, n * sizeof(int));
-    if (err != cudaSuccess) {
-        cudaGetLastError();
-        if (dp) cudaFree(dp);
-        return fail(MCB_ERR_NOMEM, "cudaMalloc for %zu trajectory points failed: %s", n, cudaGetErrorString(err));
+    if (n_paths == 0) return MCB_OK;
+    // Host destination: rows are pure functions of (seed, path id), so the job is cut into slabs of
+    // <= 128 MB that go through the engine's grow-only workspace (no per-call cudaMalloc / cudaFree,
+    // bounded device memory whatever n_paths is) and are copied back slab by slab.
+    const size_t row = (size_t)opt->N_STEPS;
+    uint64_t slab_rows = ((size_t)32 << 20) / row;   // 32 Mi floats = 128 MB per array
+    if (slab_rows < 1) slab_rows = 1;
+    if (slab_rows > n_paths) slab_rows = n_paths;
+    const size_t slab_elems = (((size_t)slab_rows * row) + 3) & ~(size_t)3;   // keeps the second array 16-byte aligned
+    if ((rc = e->traj_ws.reserve(slab_elems * (counts ? 2 : 1)))) return rc;
+    float *dp = e->traj_ws.ptr;
+    int *dc = counts ? reinterpret_cast<int *>(e->traj_ws.ptr + slab_elems) : nullptr;
+    for (uint64_t done = 0; done < n_paths; done += slab_rows) {
+        const uint64_t rows = n_paths - done < slab_rows ? n_paths - done : slab_rows;
+        if ((rc = mcb_trajectories_async(e, opt, first_path + done, rows, seed, dp, dc, nullptr))) return rc;
+        const size_t off = (size_t)done * row, cnt = (size_t)rows * row;
+        CU(cudaMemcpyAsync(prices + off, dp, cnt * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+        if (counts) CU(cudaMemcpyAsync(counts + off, dc, cnt * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaStreamSynchronize(e->stream));   // the workspace is reused by the next slab
     }
-    rc = mcb_trajectories_async(e, opt, first_path, n_paths, seed, dp, dc, nullptr);
-    if (rc == MCB_OK) {
-        err = cudaMemcpyAsync(prices, dp, n * sizeof(float), cudaMemcpyDeviceToHost, e->stream);
-        if (err == cudaSuccess && counts)
-            err = cudaMemcpyAsync(counts, dc, n * sizeof(int), cudaMemcpyDeviceToHost, e->stream);
-        if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
-        if (err != cudaSuccess) rc = fail(MCB_ERR_CUDA, "trajectory copy-back failed: %s", cudaGetErrorString(err));
-    }
-    cudaFree(dp);
-    if (dc) cudaFree(dc);
-    return rc;
+    return MCB_OK;
 }
 
 // ---------------------------------------------------------------------------------- nested MC

@@ -668,3 +668,15 @@ def test_engine_vs_the_reference_gpu_wrappers(engine, orc, pkg):
     # both estimators have the engine's SE at this N (same payoff distribution): difference ~ sqrt(2) SE
     assert abs(ref_vanilla - mine_v.price) < 4.0 * np.sqrt(2.0) * mine_v.std_error + 1e-3, (ref_vanilla, mine_v)
     assert abs(ref_bullet - mine_b.price) < 4.0 * np.sqrt(2.0) * mine_b.std_error + 1e-3, (ref_bullet, mine_b)
+
+
+def test_trajectories_to_host_in_slabs(engine, pkg):
+    """A host-destination request larger than the 128 MB workspace slab (2^18 rows x 252 steps = 264 MB,
+    + counts) is produced slab by slab; rows must not depend on where the slab boundaries fall."""
+    n, steps = 1 << 18, 252
+    opt = pkg.option(N_STEPS=steps, N_PATHS=n, B=120.0)
+    prices, counts = engine.simulate_trajectories(opt, 5, n, 1234, want_counts=True)
+    assert np.isfinite(prices).all() and (counts >= 0).all() and (np.diff(counts, axis=1) >= 0).all()
+    for lo in (0, 133150, 133160, n - 10):      # 133 152 rows per slab: straddle the first boundary
+        p2, c2 = engine.simulate_trajectories(opt, 5 + lo, 10, 1234, want_counts=True)
+        assert (p2.view(np.uint32) == prices[lo:lo + 10].view(np.uint32)).all() and (c2 == counts[lo:lo + 10]).all()
