@@ -506,6 +506,25 @@ def other_workloads(torch, pkg, eng, hbm_gbs, peak_src):
                                                 "GB_per_s": 2 * nbytes / t2 / 1e9, "ms": 1e3 * t2}
     del buf, cnt
 
+    # pre-generated-normal pricing: 2^20 paths x 252 normals read from HBM (1.06 GB)
+    import ctypes as C
+    zbuf = torch.empty(TRAJ_PATHS * TRAJ_STEPS, dtype=torch.float32, device="cuda")
+    pay = torch.empty(TRAJ_PATHS, dtype=torch.float32, device="cuda")
+    lib = pkg.load_library()
+    assert lib.mcb_generate_normals(eng._h, SEED, TRAJ_PATHS * TRAJ_STEPS, zbuf.data_ptr(), pkg.DEVICE) == 0
+    pre = lambda: lib.mcb_price_from_normals(eng._h, C.byref(opt), zbuf.data_ptr(), TRAJ_PATHS, TRAJ_STEPS,
+                                             pay.data_ptr(), pkg.DEVICE)
+    for _ in range(3):
+        assert pre() == 0
+    t0 = time.perf_counter()
+    for _ in range(20):
+        pre()
+    tp = (time.perf_counter() - t0) / 20
+    out["pregenerated_normals_2^20x252"] = {"GB_per_s_read": nbytes / tp / 1e9, "ms": 1e3 * tp,
+                                            "frac_of_hbm": nbytes / tp / 1e9 / hbm_gbs,
+                                            "note": "synchronous call (launch + sync included), 4 B read per path-step"}
+    del zbuf, pay
+
     # bullet option, 2^24 paths x 100 steps (hello.cu parameters, r as configs[0]); 16 384 CTAs = 18 waves
     ob = pkg.option(N_STEPS=100, N_PATHS=1 << 24, B=120.0, P1=10, P2=50, **CFG)
     seg = torch.zeros(2 * pkg.SEGMENTS, dtype=torch.float64, device="cuda")

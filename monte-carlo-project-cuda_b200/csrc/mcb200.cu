@@ -1082,7 +1082,8 @@ int mcb_price_from_normals(mcb_engine *e, const mcb_option_data *opt, const floa
         dz = base;
         dp = base + nz;
     }
-    const uint64_t ctas = (n_paths + kSlots - 1) / kSlots;
+    const uint64_t ctas = (n_paths + kWarps - 1) / kWarps;   // one warp per path
+    if (ctas > 0x7fffffffull) return fail(MCB_ERR_INVALID, "too many paths for one launch");
     pregen_kernel<<<(unsigned)ctas, kSlots, 0, e->stream>>>(dz, n_paths, n_steps, w.l0, w.dr, w.v, opt->K, dp);
     e->launches++;
     CU(cudaGetLastError());

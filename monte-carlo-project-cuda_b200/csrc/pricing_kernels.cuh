@@ -521,17 +521,34 @@ reduce_blocks_kernel(const float *__restrict__ x, uint64_t n, uint64_t span, int
     if (threadIdx.x == 0) out[blockIdx.x] = a;
 }
 
-// Pricing from pre-generated normals (inc/trajectories.cuh:14-52): thread per path.
+// Pricing from pre-generated normals normals[p*n_steps + i] (inc/trajectories.cuh:14-52).  The
+// reference gives a thread a path, so a warp's loads are n_steps*4 bytes apart (32 sectors per
+// load); here a WARP takes a path: lane j sums steps j, j+32, ... (coalesced 128-byte loads), the
+// lane sums fold 16,8,4,2,1.  Only the terminal price matters, so the walk is one dot product:
+//   log2 S_T = log2 S_0 + n_steps*dr + v * sum_i z_i.
 __global__ void __launch_bounds__(kSlots)
 pregen_kernel(const float *__restrict__ normals, uint64_t n_paths, int n_steps, float l0, float dr, float v,
               float K, float *__restrict__ payoffs)
 {
-    const uint64_t p = (uint64_t)blockIdx.x * kSlots + threadIdx.x;
-    if (p >= n_paths) return;
-    float l = l0;
+    const int lane = threadIdx.x & 31;
+    const uint64_t p = (uint64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
+    if (p >= n_paths) return;   // warp-uniform
     const float *z = normals + p * (uint64_t)n_steps;
-    for (int i = 0; i < n_steps; ++i) l = fmaf(v, z[i], l) + dr;
-    payoffs[p] = fmaxf(mufu_ex2(l) - K, 0.0f);
+    float acc = 0.0f;
+    if ((n_steps & 3) == 0 && ((uintptr_t)normals & 15) == 0) {   // rows are 16-byte aligned: 128-bit loads
+        const float4 *z4 = reinterpret_cast<const float4 *>(z);
+        for (int i = lane; i < (n_steps >> 2); i += 32) {
+            const float4 q = __ldcs(z4 + i);
+            acc = acc + ((q.x + q.y) + (q.z + q.w));
+        }
+    } else {
+        for (int i = lane; i < n_steps; i += 32) acc = acc + __ldcs(z + i);
+    }
+    acc = warp_fold(acc);
+    if (lane == 0) {
+        const float l = fmaf(v, acc, fmaf((float)n_steps, dr, l0));
+        payoffs[p] = fmaxf(mufu_ex2(l) - K, 0.0f);
+    }
 }
 
 // ---- parity hooks ---------------------------------------------------------------------
