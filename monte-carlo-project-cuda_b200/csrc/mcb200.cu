@@ -311,11 +311,14 @@ void launch_trajectory(const PathParams &prm, uint64_t n_paths, bool vec, float 
         if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
         kern<<<(unsigned)ctas, kSlabWarps * 32, smem, st>>>(prm, d_prices, d_counts, d_logs);                 \
     } while (0)
-    if (vec && prm.n_steps > SPL * LPR && multi_smem <= (n_arrays == 1 ? 48 : 72) * 1024) {
-        if (d_counts && d_logs) MCB_SLAB(kRowsPerWarp, true, true, true);
-        else if (d_counts) MCB_SLAB(kRowsPerWarp, true, false, true);
-        else if (d_logs) MCB_SLAB(kRowsPerWarp, false, true, true);
-        else MCB_SLAB(kRowsPerWarp, false, false, true);
+    // (only the largest layout is ever asked for rows longer than its pass)
+    if (SPL * LPR == 256 && vec && prm.n_steps > SPL * LPR && multi_smem <= (n_arrays == 1 ? 48 : 72) * 1024) {
+        if constexpr (SPL * LPR == 256) {
+            if (d_counts && d_logs) MCB_SLAB(kRowsPerWarp, true, true, true);
+            else if (d_counts) MCB_SLAB(kRowsPerWarp, true, false, true);
+            else if (d_logs) MCB_SLAB(kRowsPerWarp, false, true, true);
+            else MCB_SLAB(kRowsPerWarp, false, false, true);
+        }
     } else if (vec && prm.n_steps <= SPL * LPR) {
         // rows per slab: ~6 for one output array (tuned on B200 at 2^20 x 252, profiles/r1_trajectory_tuning.txt),
         // fewer when counts / logs need their own staging rows; always a whole number of passes
