@@ -196,6 +196,31 @@ def reference_gpu_baseline(n_paths: int = 1 << 26):
         return {"error": repr(exc)}
 
 
+def reference_bullet_rate(threads: int, paths_per_thread: int = 1 << 17):
+    """The unmodified reference CPU bullet pricer (simulateBulletOptionPriceCPU, inc/tool.cuh:133-173),
+    100 steps, on `threads` host threads: path-steps/s.  None without oracle/_ref."""
+    import ctypes as C
+    import oracle
+    if not oracle.have_ref():
+        return None
+    ref = oracle.ref_cpu()
+    o = oracle.option(N_PATHS=paths_per_thread, N_STEPS=100, B=120.0, P1=10, P2=50, **CFG)
+    out = [0.0] * threads
+
+    def work(i):
+        out[i] = ref.ref_bullet_cpu(C.byref(o))
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
+    t0 = time.perf_counter()
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    dt = time.perf_counter() - t0
+    return {"path_steps_per_s": threads * paths_per_thread * 100 / dt, "cores": threads, "price": sum(out) / threads,
+            "sample": f"{threads} threads x {paths_per_thread} paths x 100 steps ({dt:.1f} s)"}
+
+
 def host_threads():
     try:
         return max(1, len(os.sched_getaffinity(0)))
@@ -426,6 +451,9 @@ def run_b200(args):
             "sample": f"{threads} threads x {per_thread} paths ({dt:.1f} s) of the 2^30-path workload, "
                       f"calls of 2^20 paths", "value_1core": rate1, "price": price,
         }
+        bullet_cpu = reference_bullet_rate(threads)
+        if bullet_cpu:
+            line["cpu_baseline"]["bullet"] = bullet_cpu
 
     # ---- the reference's own GPU wrappers on this same GPU (rank 0, N = 1 only; context, not a target) ----
     if world == 1 and rank == 0 and not args.no_cpu_baseline:
@@ -469,7 +497,8 @@ def other_workloads(torch, pkg, eng, hbm_gbs, peak_src):
         r0 = eng.price_european(o0, 0, SEED, pkg.CALL)
     dt0 = (time.perf_counter() - t0) / 200
     out["european_1e6_sync_call"] = {"us_per_call": 1e6 * dt0, "paths_per_s": 1e6 / dt0, "price": r0.price,
-                                     "std_error": r0.std_error, "closed_form": bs_call(**CFG)}
+                                     "std_error": r0.std_error, "closed_form": bs_call(**CFG),
+                                     "z_score": (r0.price - bs_call(**CFG)) / r0.std_error}
 
     # configs[2]: 2^20 paths x 252 steps stored path-major to HBM (1.06 GB per launch > 126 MB L2)
     opt = pkg.option(N_STEPS=TRAJ_STEPS, N_PATHS=TRAJ_PATHS, B=120.0, **CFG)
@@ -532,7 +561,8 @@ def other_workloads(torch, pkg, eng, hbm_gbs, peak_src):
     walk_bound = 148 * 30.0 * 1.965e9 / 4.75   # fmaheavy: ~4.75 IMAD.WIDE per step at ~30 /clk/SM (measured)
     out["bullet_2^24x100"] = {"path_steps_per_s": (1 << 24) * 100 / t, "ms": 1e3 * t,
                               "bound": "fmaheavy: 4.75 IMAD.WIDE per path-step at 30/clk/SM (measured) = 1.84e12 /s",
-                              "frac": (1 << 24) * 100 / t / walk_bound}
+                              "frac": (1 << 24) * 100 / t / walk_bound,
+                              "frac_of_issue_bound_2.0e12": (1 << 24) * 100 / t / 2.0e12}
 
     # configs[3]: nested MC 4096 outer x 4096 inner x 100 steps = 8.30e10 inner path-steps
     on = pkg.option(N_STEPS=100, N_PATHS=4096, N_PATHS_INNER=4096, B=120.0, P1=10, P2=50, **CFG)
