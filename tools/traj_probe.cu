@@ -115,6 +115,57 @@ void run_split(float *out, float *sink)
            (double)(1 << 20) * 256 / ms / 1e9, cudaGetErrorString(cudaGetLastError()));
 }
 
+// Thread-per-path experiment: lane = row, serial walk (no prefix / scan), TS steps staged per tile in
+// shared memory (padded rows, conflict-free STS.128), every lane hands its own row segment to the TMA
+// engine (cp.async.bulk of TS*4 bytes), double-buffered tiles.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+template <int TS>
+__global__ void __launch_bounds__(128) probe_rows(PhiloxKeys keys, float sc, float dr, float *out)
+{
+    constexpr int kStride = TS + 4;
+    __shared__ __align__(128) float tile[4][2][32][kStride];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t row = (blockIdx.x * 4 + warp) * 32 + lane;
+    float l = 6.64f;
+    for (int t = 0; t < 256 / TS; ++t) {
+        float *buf = &tile[warp][t & 1][lane][0];
+        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // my copy from two tiles ago has been read
+#pragma unroll 2
+        for (int b = 0; b < TS / 4; ++b) {
+            float d[4];
+            increments4(philox4x32_10((uint32_t)(t * (TS / 4) + b), 0u, row, 0u, keys), sc, dr, d);
+            float4 s;
+            l += d[0]; s.x = mufu_ex2(l);
+            l += d[1]; s.y = mufu_ex2(l);
+            l += d[2]; s.z = mufu_ex2(l);
+            l += d[3]; s.w = mufu_ex2(l);
+            *reinterpret_cast<float4 *>(buf + 4 * b) = s;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        float *dst = out + (size_t)row * 256 + t * TS;
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(dst), "r"(smem_u32(buf)), "r"(TS * 4) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+template <int TS>
+void run_rows(float *out)
+{
+    const int blocks = (1 << 20) / 128;
+    PhiloxKeys k = make_philox_keys(1234);
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    for (int i = 0; i < 3; ++i) probe_rows<TS><<<blocks, 128>>>(k, 0.0214f, 1.6e-4f, out);
+    cudaEventRecord(a);
+    for (int i = 0; i < 20; ++i) probe_rows<TS><<<blocks, 128>>>(k, 0.0214f, 1.6e-4f, out);
+    cudaEventRecord(b);
+    cudaEventSynchronize(b);
+    float ms; cudaEventElapsedTime(&ms, a, b); ms /= 20;
+    printf("ROWS: thread per path, tile %3d steps + per-lane bulk %8.1f us  %6.3f Tsteps/s  %s\n", TS, ms * 1e3,
+           (double)(1 << 20) * 256 / ms / 1e9, cudaGetErrorString(cudaGetLastError()));
+}
+
 template <int WHAT>
 void run(const char *name, float *out, float *sink)
 {
@@ -151,6 +202,9 @@ int main()
     run<BOXMULLER | PREFIX | EXP2>("fp only: bm + prefix + ex2 (no scan)", out, sink);
     run<BOXMULLER | PREFIX | SCAN | EXP2>("fp only: bm + prefix + scan + ex2", out, sink);
     run_split(out, sink);
+    run_rows<16>(out);
+    run_rows<32>(out);
+
     run<STORE>("stores only", out, sink);
     run<EXP2 | STORE>("ex2 + stores", out, sink);
     return 0;
