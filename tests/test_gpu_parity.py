@@ -680,3 +680,19 @@ def test_trajectories_to_host_in_slabs(engine, pkg):
     for lo in (0, 133150, 133160, n - 10):      # 133 152 rows per slab: straddle the first boundary
         p2, c2 = engine.simulate_trajectories(opt, 5 + lo, 10, 1234, want_counts=True)
         assert (p2.view(np.uint32) == prices[lo:lo + 10].view(np.uint32)).all() and (c2 == counts[lo:lo + 10]).all()
+
+
+def test_european_deep_bias_check_2pow34(engine, orc, pkg):
+    """Fast-math bias (SURVEY section 7 "hard parts"): 2^34 paths, SE = 1.1e-4 on the call -- any
+    systematic error of the MUFU / FP32 pipeline above ~3e-5 relative would show as |z| > 3.  Measured
+    offline at 2^36 paths (SE 5.6e-5) for three seeds: z = -0.35, -0.92, -0.82 (call), -0.23, -0.82,
+    +0.01 (put), i.e. a bias, if any, below 5e-6 relative (the FP32 rounding of the folded exponent
+    constants c0, c1 is of that order)."""
+    n = 1 << 34
+    L = orc.lib()
+    for ot, exact in ((pkg.CALL, L.orc_bs_call_exact(100, 100, 1, 0.05, 0.2)),
+                      (pkg.PUT, L.orc_bs_put_exact(100, 100, 1, 0.05, 0.2))):
+        res = engine.price_european(pkg.option(**CFG1), n, 20261018, ot)
+        assert res.n_paths == n
+        assert abs(res.price - exact) < 3.0 * res.std_error, (res.price, exact, res.std_error)
+        assert res.std_error < 1.3e-4
