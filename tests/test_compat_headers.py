@@ -171,3 +171,19 @@ def test_c_abi_from_plain_c_runs(pkg, engine):
     rows = engine.simulate_trajectories(opt, 0, 8, 1234)
     assert np.float32(first) == rows[0, 0] and np.float32(last) == rows[7, 99]
     assert abs((call - put) - (100.0 - 100.0 * np.exp(-0.05))) < 4 * 20.0 / 1024
+
+
+def test_cmake_build_with_the_reference_targets(tmp_path):
+    """CMakeLists.txt: the engine, the examples and -- with -DMCB_REFERENCE_DIR -- the reference's own
+    `main` / `test` targets (CMakeLists.txt:20-21 of the reference) configure and build for sm_100a."""
+    import shutil
+    if not (shutil.which("cmake") and shutil.which("ninja")):
+        pytest.skip("cmake / ninja not on PATH")
+    args = ["cmake", "-S", ROOT, "-B", str(tmp_path), "-G", "Ninja"]
+    have_ref = os.path.exists("/root/reference/hello.cu")
+    if have_ref:
+        args.append("-DMCB_REFERENCE_DIR=/root/reference")
+    subprocess.run(args, check=True, capture_output=True)
+    subprocess.run(["cmake", "--build", str(tmp_path), "-j", "4"], check=True, capture_output=True)
+    for name in ["libmcb200.so", "hello_b200", "testing_b200"] + (["main", "test"] if have_ref else []):
+        assert os.path.exists(tmp_path / name), name
