@@ -921,7 +921,13 @@ int mcb_nested_async(mcb_engine *e, const mcb_option_data *opt, uint64_t first_o
     {
         cudaStream_t st = pick(e, stream);
         TimedScope timed(e, MCB_KERNEL_NESTED, st);
-        nested_kernel<<<(unsigned)n_outer, kSlots, 0, st>>>(prm, ws_logs, ws_counts, d_F);
+        // points of one outer trajectory are spread over `split` CTAs (interleaved k): at least 8 (C4:
+        // 56.9 -> 54.2 ms), more when there are few outer trajectories, so the grid stays at >= ~8 waves
+        const uint64_t want = 8ull * 5ull * (uint64_t)e->prop.multiProcessorCount;
+        uint64_t split = (want + n_outer - 1) / n_outer;
+        if (split < 8) split = 8;
+        if (split > (uint64_t)opt->N_STEPS) split = (uint64_t)opt->N_STEPS;
+        nested_kernel<<<dim3((unsigned)n_outer, (unsigned)split), kSlots, 0, st>>>(prm, ws_logs, ws_counts, d_F);
     }
     e->launches++;
     CU(cudaGetLastError());

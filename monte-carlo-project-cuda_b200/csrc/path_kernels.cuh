@@ -380,8 +380,11 @@ nested_kernel(const __grid_constant__ NestedParams prm, const float *__restrict_
     const int n_steps = prm.n_steps;
     const uint64_t row = (uint64_t)blockIdx.x * (uint64_t)n_steps;
 
+    // gridDim.y CTAs share an outer trajectory, taking its points k = y, y + gridDim.y, ...: F[p,k]
+    // depends on (p, k) only, and the interleaved split balances the work (a point costs
+    // N_STEPS - 1 - k inner steps) while giving the scheduler more, shorter CTAs for the tail
 #pragma unroll 1
-    for (int k = 0; k < n_steps; ++k) {
+    for (int k = (int)blockIdx.y; k < n_steps; k += (int)gridDim.y) {
         const float lo = __ldg(logs + row + k);
         const int co = __ldg(counts + row + k);
         const int remaining = n_steps - (k + 1);
