@@ -696,3 +696,40 @@ def test_european_deep_bias_check_2pow34(engine, orc, pkg):
         assert res.n_paths == n
         assert abs(res.price - exact) < 3.0 * res.std_error, (res.price, exact, res.std_error)
         assert res.std_error < 1.3e-4
+
+
+def test_two_engines_from_two_host_threads(pkg):
+    """One engine = one host thread at a time; two engines on the same GPU from two threads must not
+    interfere (own stream, own workspaces, thread-local error string) and give the serial bits."""
+    import threading
+    opt = pkg.option(**CFG1)
+    serial = pkg.Engine(0)
+    want = [serial.price_european(opt, 3_000_000 + i, 1234 + i, pkg.CALL) for i in range(6)]
+    want_b = serial.price_bullet(pkg.option(N_STEPS=50, B=120.0, P1=5, P2=40), 200_000, 7)
+    serial.close()
+    got = {}
+
+    def worker(tid):
+        eng = pkg.Engine(0)
+        out = []
+        for rep in range(3):
+            for i in range(6):
+                out.append(eng.price_european(opt, 3_000_000 + i, 1234 + i, pkg.CALL))
+            out.append(eng.price_bullet(pkg.option(N_STEPS=50, B=120.0, P1=5, P2=40), 200_000, 7))
+            with pytest.raises(pkg.McbError):
+                eng.price_european(pkg.option(S0=-1.0), 10, 1, pkg.CALL)   # errors stay per-thread
+        got[tid] = out
+        eng.close()
+
+    ts = [threading.Thread(target=worker, args=(t,)) for t in range(2)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    for tid in range(2):
+        out = got[tid]
+        for rep in range(3):
+            for i in range(6):
+                r = out[rep * 7 + i]
+                assert r.sum == want[i].sum and r.sumsq == want[i].sumsq
+            assert out[rep * 7 + 6].sum == want_b.sum
