@@ -289,8 +289,8 @@ __global__ void curand_blocks_kernel(uint64_t seed, const uint64_t *__restrict__
 // pass and is 16-byte aligned (the bandwidth path, config 3; counts and log2 prices ride along in
 // their own staging rows), the general kernel otherwise.
 template <int SPL, int LPR>
-void launch_trajectory(const PathParams &prm, uint64_t n_paths, bool vec, float *d_prices, int *d_counts,
-                              float *d_logs, cudaStream_t st)
+void launch_trajectory(const PathParams &prm, uint64_t n_paths, bool vec, bool base_aligned, float *d_prices,
+                       int *d_counts, float *d_logs, cudaStream_t st)
 {
     constexpr int kRowsPerWarp = 32 / LPR;
     constexpr int kSlabWarps = 4;
@@ -301,9 +301,9 @@ void launch_trajectory(const PathParams &prm, uint64_t n_paths, bool vec, float 
     // rows take the general kernel
     const int n_arrays = 1 + (d_counts ? 1 : 0) + (d_logs ? 1 : 0);
     const size_t multi_smem = (size_t)kSlabWarps * n_arrays * kRowsPerWarp * (size_t)prm.n_steps * sizeof(float);
-#define MCB_SLAB(ROWS, CNT, LOG, MULTI)                                                                       \
+#define MCB_SLAB(ROWS, CNT, LOG, MULTI, ALIGNED)                                                              \
     do {                                                                                                      \
-        auto kern = trajectory_slab_kernel<SPL, LPR, ROWS, kSlabWarps, CNT, LOG, MULTI>;                      \
+        auto kern = trajectory_slab_kernel<SPL, LPR, ROWS, kSlabWarps, CNT, LOG, MULTI, ALIGNED>;             \
         const uint64_t rows_per_cta = (uint64_t)kSlabWarps * ROWS;                                            \
         const uint64_t ctas = (n_paths + rows_per_cta - 1) / rows_per_cta;                                    \
         const size_t smem = (size_t)kSlabWarps * (1 + (CNT ? 1 : 0) + (LOG ? 1 : 0)) * ROWS *                 \
@@ -314,10 +314,10 @@ void launch_trajectory(const PathParams &prm, uint64_t n_paths, bool vec, float 
     // (only the largest layout is ever asked for rows longer than its pass)
     if (SPL * LPR == 256 && vec && prm.n_steps > SPL * LPR && multi_smem <= (n_arrays == 1 ? 48 : 72) * 1024) {
         if constexpr (SPL * LPR == 256) {
-            if (d_counts && d_logs) MCB_SLAB(kRowsPerWarp, true, true, true);
-            else if (d_counts) MCB_SLAB(kRowsPerWarp, true, false, true);
-            else if (d_logs) MCB_SLAB(kRowsPerWarp, false, true, true);
-            else MCB_SLAB(kRowsPerWarp, false, false, true);
+            if (d_counts && d_logs) MCB_SLAB(kRowsPerWarp, true, true, true, true);
+            else if (d_counts) MCB_SLAB(kRowsPerWarp, true, false, true, true);
+            else if (d_logs) MCB_SLAB(kRowsPerWarp, false, true, true, true);
+            else MCB_SLAB(kRowsPerWarp, false, false, true, true);
         }
     } else if (vec && prm.n_steps <= SPL * LPR) {
         // rows per slab: ~6 for one output array (tuned on B200 at 2^20 x 252, profiles/r1_trajectory_tuning.txt),
@@ -325,10 +325,17 @@ void launch_trajectory(const PathParams &prm, uint64_t n_paths, bool vec, float 
         constexpr int kRows1 = (6 + kRowsPerWarp - 1) / kRowsPerWarp * kRowsPerWarp;
         constexpr int kRows2 = (4 + kRowsPerWarp - 1) / kRowsPerWarp * kRowsPerWarp;
         constexpr int kRows3 = (2 + kRowsPerWarp - 1) / kRowsPerWarp * kRowsPerWarp;
-        if (d_counts && d_logs) MCB_SLAB(kRows3, true, true, false);
-        else if (d_counts) MCB_SLAB(kRows2, true, false, false);
-        else if (d_logs) MCB_SLAB(kRows2, false, true, false);
-        else MCB_SLAB(kRows1, false, false, false);
+        if (d_counts && d_logs) MCB_SLAB(kRows3, true, true, false, true);
+        else if (d_counts) MCB_SLAB(kRows2, true, false, false, true);
+        else if (d_logs) MCB_SLAB(kRows2, false, true, false, true);
+        else MCB_SLAB(kRows1, false, false, false, true);
+    } else if (base_aligned && prm.n_steps <= SPL * LPR) {
+        // rows that are not a multiple of 4 floats (150, 250 steps ...): slabs of 8 / 4 rows start on
+        // 16-byte boundaries, so the bulk store still applies; only the staging is element-wise
+        if (d_counts && d_logs) MCB_SLAB(4, true, true, false, false);
+        else if (d_counts) MCB_SLAB(4, true, false, false, false);
+        else if (d_logs) MCB_SLAB(4, false, true, false, false);
+        else MCB_SLAB(8, false, false, false, false);
 #undef MCB_SLAB
     } else {
         const uint64_t rows_per_cta = (uint64_t)kPathWarps * kPathsPerWarp * kRowsPerWarp;
@@ -820,8 +827,9 @@ static int trajectories_launch(mcb_engine *e, const mcb_option_data *opt, uint64
     prm.n_paths = n_paths;
     prm.keys = make_philox_keys(seed);
     if (n_paths > 0x7fffffffull) return fail(MCB_ERR_INVALID, "too many paths for one launch");
-    const bool vec = (opt->N_STEPS % 4 == 0) && ((uintptr_t)d_prices % 16 == 0) &&
-                     (!d_counts || (uintptr_t)d_counts % 16 == 0) && (!d_logs || (uintptr_t)d_logs % 16 == 0);
+    const bool base_aligned = ((uintptr_t)d_prices % 16 == 0) && (!d_counts || (uintptr_t)d_counts % 16 == 0) &&
+                              (!d_logs || (uintptr_t)d_logs % 16 == 0);
+    const bool vec = (opt->N_STEPS % 4 == 0) && base_aligned;
     cudaStream_t st = pick(e, stream);
     {
         TimedScope timed(e, MCB_KERNEL_TRAJECTORY, st);
@@ -829,11 +837,11 @@ static int trajectories_launch(mcb_engine *e, const mcb_option_data *opt, uint64
         // bits never depend on which arrays were asked for or which kernel wrote it: the smallest
         // pass that holds the whole row, 16 x 16 (several passes) beyond 256 steps.
         const int n = opt->N_STEPS;
-        if (n <= 32) launch_trajectory<4, 8>(prm, n_paths, vec, d_prices, d_counts, d_logs, st);
-        else if (n <= 64) launch_trajectory<4, 16>(prm, n_paths, vec, d_prices, d_counts, d_logs, st);
-        else if (n <= 128) launch_trajectory<8, 16>(prm, n_paths, vec, d_prices, d_counts, d_logs, st);
-        else if (n <= 192) launch_trajectory<12, 16>(prm, n_paths, vec, d_prices, d_counts, d_logs, st);
-        else launch_trajectory<16, 16>(prm, n_paths, vec, d_prices, d_counts, d_logs, st);
+        if (n <= 32) launch_trajectory<4, 8>(prm, n_paths, vec, base_aligned, d_prices, d_counts, d_logs, st);
+        else if (n <= 64) launch_trajectory<4, 16>(prm, n_paths, vec, base_aligned, d_prices, d_counts, d_logs, st);
+        else if (n <= 128) launch_trajectory<8, 16>(prm, n_paths, vec, base_aligned, d_prices, d_counts, d_logs, st);
+        else if (n <= 192) launch_trajectory<12, 16>(prm, n_paths, vec, base_aligned, d_prices, d_counts, d_logs, st);
+        else launch_trajectory<16, 16>(prm, n_paths, vec, base_aligned, d_prices, d_counts, d_logs, st);
     }
     e->launches++;
     CU(cudaGetLastError());

@@ -259,7 +259,11 @@ trajectory_kernel(const __grid_constant__ PathParams prm, float *__restrict__ pr
 // the L1->L2 crossbar, no per-row address arithmetic, one fence per slab.
 // Dynamic shared memory: WARPS * arrays * ROWS * n_steps floats.
 // ------------------------------------------------------------------------------------------
-template <int SPL, int LPR, int ROWS, int WARPS, bool COUNTS, bool LOGS, bool MULTI = false>
+// ALIGNED: n_steps % 4 == 0, every row is 16-byte aligned and the lanes stage with STS.128.
+// Otherwise (150- or 250-step rows ...) the lanes stage element by element, ROWS is a multiple
+// of 4 so that every SLAB still starts on a 16-byte boundary of the output, the bulk store takes
+// the slab's whole 16-byte units and one lane writes the last one to three floats of a ragged slab.
+template <int SPL, int LPR, int ROWS, int WARPS, bool COUNTS, bool LOGS, bool MULTI = false, bool ALIGNED = true>
 __global__ void __launch_bounds__(WARPS * 32)
 trajectory_slab_kernel(const __grid_constant__ PathParams prm, float *__restrict__ prices, int *__restrict__ counts,
                        float *__restrict__ logs)
@@ -268,6 +272,7 @@ trajectory_slab_kernel(const __grid_constant__ PathParams prm, float *__restrict
     constexpr int kRowsPerWarp = 32 / LPR;
     constexpr int kArrays = 1 + (COUNTS ? 1 : 0) + (LOGS ? 1 : 0);
     static_assert(ROWS % kRowsPerWarp == 0, "a slab is a whole number of passes");
+    static_assert(ALIGNED || ROWS % 4 == 0, "unaligned rows: slabs must start on 16-byte boundaries");
     extern __shared__ __align__(128) float stage[];    // [warp][array][ROWS][n_steps]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sub = lane / LPR, ln = lane % LPR;
@@ -319,20 +324,32 @@ trajectory_slab_kernel(const __grid_constant__ PathParams prm, float *__restrict
                 for (int b = 0; b < kBlocks; ++b) {
                     if (my_step + 4 * b < n_steps) {
                         int c[4];
-                        if (COUNTS) {
+                        float s4[4];
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
+                        for (int j = 0; j < 4; ++j) {
+                            s4[j] = mufu_ex2(a[4 * b + j]);
+                            if (COUNTS) {
                                 cbase += (a[4 * b + j] < prm.lB) ? 1 : 0;
                                 c[j] = cbase;
                             }
-                            *reinterpret_cast<int4 *>(dst + slab_floats + 4 * b) = make_int4(c[0], c[1], c[2], c[3]);
                         }
-                        if (LOGS)
-                            *reinterpret_cast<float4 *>(dst + (COUNTS ? 2 : 1) * slab_floats + 4 * b) =
-                                make_float4(a[4 * b], a[4 * b + 1], a[4 * b + 2], a[4 * b + 3]);
-                        *reinterpret_cast<float4 *>(dst + 4 * b) =
-                            make_float4(mufu_ex2(a[4 * b]), mufu_ex2(a[4 * b + 1]), mufu_ex2(a[4 * b + 2]),
-                                        mufu_ex2(a[4 * b + 3]));
+                        if (ALIGNED) {
+                            if (COUNTS)
+                                *reinterpret_cast<int4 *>(dst + slab_floats + 4 * b) = make_int4(c[0], c[1], c[2], c[3]);
+                            if (LOGS)
+                                *reinterpret_cast<float4 *>(dst + (COUNTS ? 2 : 1) * slab_floats + 4 * b) =
+                                    make_float4(a[4 * b], a[4 * b + 1], a[4 * b + 2], a[4 * b + 3]);
+                            *reinterpret_cast<float4 *>(dst + 4 * b) = make_float4(s4[0], s4[1], s4[2], s4[3]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                if (my_step + 4 * b + j < n_steps) {
+                                    dst[4 * b + j] = s4[j];
+                                    if (COUNTS) reinterpret_cast<int *>(dst + slab_floats)[4 * b + j] = c[j];
+                                    if (LOGS) dst[(COUNTS ? 2 : 1) * slab_floats + 4 * b + j] = a[4 * b + j];
+                                }
+                            }
+                        }
                     }
                 }
             }
@@ -341,12 +358,22 @@ trajectory_slab_kernel(const __grid_constant__ PathParams prm, float *__restrict
         __syncwarp();
         if (lane == 0) {
             const uint32_t rows = min((uint32_t)ROWS, n_rows - slab_row);
-            const uint32_t bytes = rows * (uint32_t)n_steps * 4u;
+            const uint32_t floats = rows * (uint32_t)n_steps;
+            const uint32_t bytes = ALIGNED ? floats * 4u : (floats * 4u) & ~15u;   // whole 16-byte units
             const uint64_t off = (uint64_t)slab_row * (uint32_t)n_steps;
-            bulk_store(prices + off, my_stage, bytes);
-            if (COUNTS) bulk_store(counts + off, my_stage + slab_floats, bytes);
-            if (LOGS) bulk_store(logs + off, my_stage + (COUNTS ? 2 : 1) * slab_floats, bytes);
+            if (bytes) {
+                bulk_store(prices + off, my_stage, bytes);
+                if (COUNTS) bulk_store(counts + off, my_stage + slab_floats, bytes);
+                if (LOGS) bulk_store(logs + off, my_stage + (COUNTS ? 2 : 1) * slab_floats, bytes);
+            }
             bulk_commit();
+            if (!ALIGNED) {   // a ragged last slab can end in one to three floats past the last unit
+                for (uint32_t i = bytes / 4u; i < floats; ++i) {
+                    prices[off + i] = my_stage[i];
+                    if (COUNTS) counts[off + i] = reinterpret_cast<const int *>(my_stage + slab_floats)[i];
+                    if (LOGS) logs[off + i] = my_stage[(COUNTS ? 2 : 1) * slab_floats + i];
+                }
+            }
         }
     }
     if (lane == 0) bulk_wait_read<0>();   // shared memory must outlive the last copies' reads
