@@ -605,7 +605,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak (default): 2^30 paths per GPU; strong: 2^30 paths in total")
-    ap.add_argument("--transport", default="nccl", choices=["nccl", "peer"],
+    ap.add_argument("--transport", default="nccl", choices=["nccl", "peer", "fused"],
                     help="N > 1: how the 64 partial-sum segments cross GPUs: one NCCL all-reduce (default) or direct "
                          "NVLink stores into CUDA-IPC peer mailboxes from inside the segment pass")
     ap.add_argument("--headline-only", action="store_true", help="skip the other BASELINE configs")

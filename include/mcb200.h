@@ -202,6 +202,11 @@ int mcb_peer_mailbox_create(mcb_engine *e, void *handle_out);
 int mcb_peer_mailbox_connect(mcb_engine *e, int rank, int world, const void *all_handles);
 int mcb_european_peer_async(mcb_engine *e, const mcb_option_data *opt, uint64_t n_paths, uint64_t seed,
                             int option_type, mcb_result *d_results, void *stream);
+/* The same in ONE launch: the pricing kernel's last CTA per segment folds and peer-stores it, the
+ * CTA that completes the rank's last segment publishes the flag, waits for the peers and runs the
+ * final tree.  Same bits as every other path; jobs of fewer than 64 chunks use the 3-launch form. */
+int mcb_european_fused_peer_async(mcb_engine *e, const mcb_option_data *opt, uint64_t n_paths, uint64_t seed,
+                                  int option_type, mcb_result *d_results, void *stream);
 
 /* Number of kernel launches this engine has issued (bench.py's gpu_launches). */
 uint64_t mcb_launch_count(mcb_engine *e);

@@ -116,6 +116,7 @@ SIGNATURES = {
     "mcb_peer_mailbox_create": (C.c_int, [_vp, _vp]),
     "mcb_peer_mailbox_connect": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "mcb_european_peer_async": (C.c_int, [_vp, _OP, _u64, _u64, C.c_int, _vp, _vp]),
+    "mcb_european_fused_peer_async": (C.c_int, [_vp, _OP, _u64, _u64, C.c_int, _vp, _vp]),
     "mcb_launch_count": (_u64, [_vp]),
     "mcb_timing_enable": (C.c_int, [_vp, C.c_int]),
     "mcb_timing_read": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_double), C.POINTER(_u64)]),
@@ -315,8 +316,9 @@ class Engine:
             raise ValueError("need one 64-byte handle per rank")
         _check(self._lib.mcb_peer_mailbox_connect(self._h, rank, world, blob))
 
-    def european_peer_async(self, opt, n_paths, seed, option_type, d_results, stream=None):
-        _check(self._lib.mcb_european_peer_async(self._h, C.byref(opt), n_paths, seed, option_type, d_results, stream))
+    def european_peer_async(self, opt, n_paths, seed, option_type, d_results, stream=None, fused=False):
+        fn = self._lib.mcb_european_fused_peer_async if fused else self._lib.mcb_european_peer_async
+        _check(fn(self._h, C.byref(opt), n_paths, seed, option_type, d_results, stream))
 
     # ---- parity hooks ------------------------------------------------------------------------
     def philox_blocks(self, seed, subsequences, blocks, library=False):

@@ -98,6 +98,7 @@ struct mcb_engine {
     void *peer_mapped[kMaxPeers] = {};     // what cudaIpcOpenMemHandle returned (to close on destroy)
     int peer_rank = -1, peer_world = 0;
     unsigned long long peer_epoch = 0;
+    DeviceBuffer<unsigned int> seg_tickets; // fused peer kernel: per-segment arrival counters (zero between launches)
     mcb_result *h_results = nullptr;       // pinned
     size_t h_results_cap = 0;
     double *h_segments = nullptr;          // pinned, [MCB_SEGMENTS][2] of the last whole-job call
@@ -421,6 +422,7 @@ int mcb_engine_destroy(mcb_engine *e)
     for (int r = 0; r < kMaxPeers; ++r)
         if (e->peer_mapped[r]) cudaIpcCloseMemHandle(e->peer_mapped[r]);
     if (e->mailbox) cudaFree(e->mailbox);
+    e->seg_tickets.release();
     if (e->h_results) cudaFreeHost(e->h_results);
     if (e->h_segments) cudaFreeHost(e->h_segments);
     delete e;
@@ -492,7 +494,8 @@ int mcb_peer_mailbox_connect(mcb_engine *e, int rank, int world, const void *all
     }
     e->peer_rank = rank;
     e->peer_world = world;
-    e->peer_epoch = 0;
+    // peer_epoch is NOT reset: the mailbox (and the epochs already published in it) outlives a
+    // re-connect, and the flags are compared with "<", so epochs must stay monotonic per engine
     return MCB_OK;
 }
 
@@ -526,6 +529,55 @@ int mcb_european_peer_async(mcb_engine *e, const mcb_option_data *opt, uint64_t 
     const double discount = std::exp(-(double)opt->r * (double)opt->T);
     combine_peer_kernel<<<1, 32, 0, st>>>(e->mailbox, world, epoch, n_paths, discount,
                                           reinterpret_cast<ResultDev *>(d_results));
+    e->launches++;
+    CU(cudaGetLastError());
+    return MCB_OK;
+}
+
+int mcb_european_fused_peer_async(mcb_engine *e, const mcb_option_data *opt, uint64_t n_paths, uint64_t seed,
+                                  int option_type, mcb_result *d_results, void *stream)
+{
+    int rc = check_common(e, opt);
+    if (rc) return rc;
+    if (e->peer_world < 1) return fail(MCB_ERR_INVALID, "peer mailboxes are not connected");
+    if (!d_results) return fail(MCB_ERR_INVALID, "d_results is NULL");
+    if (option_type != MCB_CALL && option_type != MCB_PUT) return fail(MCB_ERR_INVALID, "bad option_type");
+    n_paths = resolve_paths(opt, n_paths);
+    const uint64_t n_chunks = (n_paths + kEuropeanChunk - 1) / kEuropeanChunk;
+    // every segment needs at least one chunk for its "last CTA" to exist: small jobs take the 3-launch path
+    if (n_chunks < (uint64_t)MCB_SEGMENTS)
+        return mcb_european_peer_async(e, opt, n_paths, seed, option_type, d_results, stream);
+    DeviceGuard g(e->device);
+    cudaStream_t st = pick(e, stream);
+    const int rank = e->peer_rank, world = e->peer_world;
+    int seg_lo, seg_hi;
+    uint64_t c_lo, c_hi;
+    segment_span(rank, world, n_chunks, &seg_lo, &seg_hi, &c_lo, &c_hi);
+    if (c_hi - c_lo > 0x7fffffffull) return fail(MCB_ERR_INVALID, "too many chunks for one launch");
+    if ((rc = e->partials.reserve((size_t)(c_hi - c_lo) + 1))) return rc;
+    if (e->seg_tickets.cap == 0) {
+        if ((rc = e->seg_tickets.reserve(MCB_SEGMENTS))) return rc;
+        CU(cudaMemsetAsync(e->seg_tickets.ptr, 0, sizeof(unsigned int) * MCB_SEGMENTS, st));
+    }
+    const EuropeanParams prm = european_params(opt, opt->K, opt->v, n_paths, seed, c_lo);
+    FusedPeerArgs args{};
+    args.n_chunks = n_chunks;
+    args.n_paths = n_paths;
+    args.discount = std::exp(-(double)opt->r * (double)opt->T);
+    args.seg_tickets = e->seg_tickets.ptr;
+    args.peers = e->peers;
+    args.out = reinterpret_cast<ResultDev *>(d_results);
+    args.epoch = ++e->peer_epoch;
+    args.seg_lo = seg_lo; args.seg_hi = seg_hi; args.rank = rank; args.world = world;
+    {
+        TimedScope timed(e, MCB_KERNEL_EUROPEAN, st);
+        if (option_type == MCB_PUT)
+            european_fused_peer_kernel<kPut, MCB_EUROPEAN_PATHS_PER_SLOT><<<(unsigned)(c_hi - c_lo), kSlots, 0, st>>>(
+                prm, args, e->partials.ptr);
+        else
+            european_fused_peer_kernel<kCall, MCB_EUROPEAN_PATHS_PER_SLOT><<<(unsigned)(c_hi - c_lo), kSlots, 0, st>>>(
+                prm, args, e->partials.ptr);
+    }
     e->launches++;
     CU(cudaGetLastError());
     return MCB_OK;

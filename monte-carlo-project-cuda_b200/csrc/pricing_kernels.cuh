@@ -494,6 +494,148 @@ combine_peer_kernel(PeerMailbox *__restrict__ mine, int world, unsigned long lon
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// ONE kernel for pricing + exchange at N > 1 (mcb_european_fused_peer_async): european_kernel's
+// chunk loop, then -- through tickets, no second launch -- the last CTA of every segment folds
+// that segment (same order as segment_kernel), stores it into every peer's mailbox over NVLink,
+// and the CTA that completes this rank's last segment publishes the epoch flag, waits (bounded)
+// for the peers' flags in its own mailbox and runs the final tree (same order as combine_kernel).
+// The cold tail lives in a __noinline__ function so that the hot loop keeps its 8 CTAs per SM.
+// ------------------------------------------------------------------------------------------
+struct FusedPeerArgs {
+    uint64_t n_chunks;              // chunks of the WHOLE job (segment boundaries are global)
+    uint64_t n_paths;
+    double discount;
+    unsigned int *seg_tickets;      // [kSegments], zero between launches
+    PeerTable peers;
+    ResultDev *out;
+    unsigned long long epoch;
+    int seg_lo, seg_hi, rank, world;
+};
+
+__device__ __noinline__ void fused_peer_tail(const FusedPeerArgs &args, const float2 *__restrict__ partials,
+                                             uint64_t first_chunk, double *dscratch, int *flag)
+{
+    const uint64_t chunk = first_chunk + blockIdx.x;
+    const uint64_t n = args.n_chunks;
+    if (threadIdx.x == 0) {
+        __threadfence();                                    // my partial is visible device-wide
+        int seg = (int)((chunk * (uint64_t)kSegments) / n);
+        while ((n * (uint64_t)(seg + 1)) / kSegments <= chunk) ++seg;
+        while ((n * (uint64_t)seg) / kSegments > chunk) --seg;
+        const uint64_t lo = (n * (uint64_t)seg) / kSegments, hi = (n * (uint64_t)(seg + 1)) / kSegments;
+        const unsigned int t = atomicAdd(&args.seg_tickets[seg], 1u);
+        flag[0] = (t == (unsigned int)(hi - lo) - 1u) ? seg : -1;
+    }
+    __syncthreads();
+    const int seg = flag[0];
+    if (seg < 0) return;                                    // CTA-uniform: not the last chunk of its segment
+    __threadfence();
+    const uint64_t lo = (n * (uint64_t)seg) / kSegments, hi = (n * (uint64_t)(seg + 1)) / kSegments;
+    double a = 0.0, b = 0.0;
+    for (uint64_t c = lo + threadIdx.x; c < hi; c += kSlots) {
+        const float2 v = __ldcg(partials + (c - first_chunk));
+        a = a + (double)v.x;
+        b = b + (double)v.y;
+    }
+    block_fold2(a, b, dscratch);
+    const int parity = (int)(args.epoch & 1ull);
+    PeerMailbox *mine = args.peers.box[args.rank];
+    if (threadIdx.x == 0) {
+        args.seg_tickets[seg] = 0u;                         // ready for the next launch
+        for (int r = 0; r < args.world; ++r) {
+            double *dst = args.peers.box[r]->gather[parity] + 2 * seg;
+            __stcg(dst, a);
+            __stcg(dst + 1, b);
+        }
+        __threadfence_system();
+        const unsigned int owned = (unsigned int)(args.seg_hi - args.seg_lo);
+        const bool last = atomicAdd(&mine->ticket, 1u) == owned - 1u;
+        if (last) {
+            mine->ticket = 0u;
+            __threadfence_system();
+            for (int r = 0; r < args.world; ++r)
+                *((volatile unsigned long long *)&args.peers.box[r]->flags[parity][args.rank]) = args.epoch;
+        }
+        flag[1] = last ? 1 : 0;
+    }
+    __syncthreads();
+    if (!flag[1] || threadIdx.x >= 32) return;
+    // the last CTA of this rank: wait for every rank's flag in MY mailbox, then the final tree
+    const int lane = threadIdx.x;
+    bool ok = true;
+    if (lane < args.world) {
+        const volatile unsigned long long *f = &mine->flags[parity][lane];
+        unsigned int spins = 0;
+        while (*f < args.epoch) {
+            if (++spins > (1u << 24)) {
+                ok = false;
+                break;
+            }
+            __nanosleep(100);
+        }
+    }
+    ok = __all_sync(kFullMask, ok);
+    __threadfence_system();
+    const volatile double *sg = mine->gather[parity];
+    double s = sg[2 * lane] + sg[2 * (lane + 32)];
+    double q = sg[2 * lane + 1] + sg[2 * (lane + 32) + 1];
+    s = warp_fold(s);
+    q = warp_fold(q);
+    if (lane == 0) {
+        const double np = (double)args.n_paths;
+        const double mean = s / np;
+        double var = q / np - mean * mean;
+        var = var > 0.0 ? var : 0.0;
+        if (args.n_paths > 1) var *= np / (np - 1.0);
+        ResultDev r;
+        r.price = args.discount * mean;
+        r.std_error = args.discount * sqrt(var / np);
+        r.sum = s;
+        r.sumsq = q;
+        r.n_paths = ok ? args.n_paths : 0;
+        args.out[0] = r;
+    }
+}
+
+template <int TYPE, int PPS>
+__global__ void __launch_bounds__(kSlots, 8)
+european_fused_peer_kernel(const __grid_constant__ EuropeanParams prm, const __grid_constant__ FusedPeerArgs args,
+                           float2 *__restrict__ partials)
+{
+    __shared__ float scratch[2 * kWarps];
+    __shared__ double dscratch[2 * kWarps];
+    __shared__ int flag[2];
+    const uint64_t chunk = prm.first_chunk + blockIdx.x;
+    const uint64_t base = chunk * (uint64_t)(kSlots * PPS);
+    const uint32_t p_hi = (uint32_t)(base >> 32);
+    const uint32_t p_lo0 = (uint32_t)base + threadIdx.x;
+    const uint64_t left = prm.n_paths - base;
+    float sum = 0.0f, sq = 0.0f;
+    if (left >= (uint64_t)(kSlots * PPS)) {
+        uint64_t prod1 = (uint64_t)kPhiloxM1 * p_lo0;
+#pragma unroll 4
+        for (int i = 0; i < PPS; ++i) {
+            const float pay = european_payoff_from_prod<TYPE>(prod1, p_hi, prm);
+            prod1 += (uint64_t)kPhiloxM1 * kSlots;
+            sum = sum + pay;
+            sq = fmaf(pay, pay, sq);
+        }
+    } else {
+        for (int i = 0; i < PPS; ++i) {
+            const uint32_t local = (uint32_t)(i * kSlots) + threadIdx.x;
+            if ((uint64_t)local < left) {
+                const float pay = european_payoff<TYPE>(p_lo0 + (uint32_t)(i * kSlots), p_hi, prm);
+                sum = sum + pay;
+                sq = fmaf(pay, pay, sq);
+            }
+        }
+    }
+    block_fold2(sum, sq, scratch);
+    if (threadIdx.x == 0) partials[blockIdx.x] = make_float2(sum, sq);
+    fused_peer_tail(args, partials, prm.first_chunk, dscratch, flag);
+}
+
 // Standalone deterministic float sum (reduce3..6 replacement): slot t adds x[t], x[t+256], ...
 __global__ void __launch_bounds__(kSlots)
 reduce_sum_kernel(const float *__restrict__ x, uint64_t n, float *__restrict__ out)

@@ -45,16 +45,17 @@ class ShardedPricer:
         self.stream = torch.cuda.Stream(self.device)
         self._reserve(max_sets)
         # transport "peer": the 64 segments are all-gathered by direct NVLink stores into CUDA-IPC
-        # mapped peer mailboxes inside the segment pass (European pricing only); "nccl": all_reduce
+        # mapped peer mailboxes inside the segment pass (European pricing only); "fused": the same from
+        # inside the pricing kernel itself (one launch per price); "nccl": all_reduce
         self.transport = transport
-        if transport == "peer" and self.world > 1:
+        if transport in ("peer", "fused") and self.world > 1:
             handle = engine.peer_mailbox_create()
             handles = [None] * self.world
             dist.all_gather_object(handles, handle, group=group)
             engine.peer_mailbox_connect(self.rank, self.world, handles)
             dist.barrier(group=group)   # every mailbox is mapped everywhere before the first store
-        elif transport not in ("nccl", "peer"):
-            raise ValueError("transport must be 'nccl' or 'peer'")
+        elif transport not in ("nccl", "peer", "fused"):
+            raise ValueError("transport must be 'nccl', 'peer' or 'fused'")
 
     def _reserve(self, n_sets: int):
         t = self.torch
@@ -78,8 +79,9 @@ class ShardedPricer:
 
     # ---- enqueue-only (device-resident result in self.results) ---------------------------
     def european_async(self, opt, n_paths, seed=1234, option_type=CALL):
-        if self.transport == "peer" and self.world > 1:
-            self.engine.european_peer_async(opt, n_paths, seed, option_type, self.results.data_ptr(), self._stream())
+        if self.transport in ("peer", "fused") and self.world > 1:
+            self.engine.european_peer_async(opt, n_paths, seed, option_type, self.results.data_ptr(), self._stream(),
+                                            fused=self.transport == "fused")
             return
         self.engine.european_segments_async(opt, n_paths, seed, option_type, self.rank, self.world,
                                             self.segments.data_ptr(), self._stream())

@@ -48,13 +48,17 @@ def _worker(rank, world, port, out_dir):
         pricer.synchronize()
         assert (lo2, n2) == (lo, hi - lo) and (dev_rows.cpu().numpy().view(np.uint32) == rows.view(np.uint32)).all()
         np.save(os.path.join(out_dir, f"F{rank}.npy"), F.cpu().numpy())
-        # NCCL-free transport: segments all-gathered by NVLink peer stores (CUDA IPC mailboxes)
+        # NCCL-free transports: segments all-gathered by NVLink peer stores (CUDA IPC mailboxes), from the
+        # segment pass ("peer") or from inside the pricing kernel itself ("fused", one launch per price)
         eng2 = pkg.Engine(rank)
-        peer = sharded.ShardedPricer(eng2, transport="peer")
         peer_out = []
-        for k in range(5):   # several epochs: parity buffers and flags are reused
-            rp = peer.price_european(opt, n + k, 1234, pkg.CALL)
-            peer_out += [rp.sum, rp.sumsq, rp.price, float(rp.n_paths)]
+        for transport in ("peer", "fused"):
+            peer = sharded.ShardedPricer(eng2, transport=transport)
+            for k in range(5):   # several epochs: parity buffers, flags and tickets are reused
+                rp = peer.price_european(opt, n + k, 1234, pkg.CALL)
+                peer_out += [rp.sum, rp.sumsq, rp.price, float(rp.n_paths)]
+            small = peer.price_european(opt, 100_000, 1234, pkg.PUT)   # < 64 chunks: 3-launch form either way
+            peer_out += [small.sum, small.sumsq, small.price, float(small.n_paths)]
         np.save(os.path.join(out_dir, f"peer{rank}.npy"), np.array(peer_out))
         dist.barrier()
         eng2.close()
@@ -89,9 +93,12 @@ def test_nccl_sharded_prices_match_single_gpu_bits(tmp_path, pkg, engine):
         got_rows.append(np.load(tmp_path / f"rows{r}.npy"))
     assert (np.concatenate(got_rows).view(np.uint32) == rows.view(np.uint32)).all()
     want_peer = []
-    for k in range(5):
-        r1 = engine.price_european(pkg.option(N_PATHS=n + k), n + k, 1234, pkg.CALL)
-        want_peer += [r1.sum, r1.sumsq, r1.price, float(n + k)]
+    for _transport in ("peer", "fused"):
+        for k in range(5):
+            r1 = engine.price_european(pkg.option(N_PATHS=n + k), n + k, 1234, pkg.CALL)
+            want_peer += [r1.sum, r1.sumsq, r1.price, float(n + k)]
+        r2 = engine.price_european(pkg.option(), 100_000, 1234, pkg.PUT)
+        want_peer += [r2.sum, r2.sumsq, r2.price, 100_000.0]
     for r in range(world):
         assert (np.load(tmp_path / f"peer{r}.npy") == np.array(want_peer)).all(), r   # bit-identical, no timeout
     nm = pkg.option(N_STEPS=12, N_PATHS=20, N_PATHS_INNER=128, B=120.0, P1=1, P2=10)
