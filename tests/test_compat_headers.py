@@ -1,5 +1,4 @@
 """include/compat: the reference's header names and wrapper_* call surface over libmcb200.so."""
-import json
 import os
 import subprocess
 

@@ -1,5 +1,4 @@
 """CPU-side checks: reduction-tree restatement, shard arithmetic, C-ABI surface."""
-import ctypes as C
 import os
 import re
 import subprocess
