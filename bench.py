@@ -1,20 +1,26 @@
 #!/usr/bin/env python
-"""bench.py -- the headline measurement: GBM paths/sec, European call, 2^30 paths per B200.
+"""bench.py -- the headline measurement: GBM paths/sec, European call, ONE 2^30-path job on N B200s.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
         --master-port P bench.py --gpus N --steps K --warmup W
 
 A "step" is one pass of the hot path: pricing a European call (BASELINE.json configs[1]:
-S0=100 K=100 r=0.05 sigma=0.2 T=1, single step) on 2^30 paths PER GPU (weak scaling: N GPUs
-price one N*2^30-path job sharded by path index, one NCCL allreduce of the 1 KiB segment vector,
-bit-identical price for any N).  Rank 0 prints ONE JSON line.
+S0=100 K=100 r=0.05 sigma=0.2 T=1, single step) on 2^30 paths.  With N GPUs the SAME 2^30-path job is
+sharded by path index (strong scaling, BASELINE.json's metric): rank g prices the chunks of its 64/N
+reduction segments in ONE kernel launch that also folds those segments and stores them into every
+rank's mailbox over NVLink; a one-warp final pass on a second stream runs the fixed tree.  The price is
+bit-identical for every N (the line carries its hex digits).  `--scaling weak` prices 2^30 paths PER
+GPU instead.  Rank 0 prints ONE JSON line.
 
-  value    : whole-job paths/s, device-timed (CUDA events, max over ranks), nothing to stage in HBM
+  value    : whole-job paths/s, device-timed with CUDA events on the engine's own streams
+             (mcb_pipeline_timer_*: from before the first pricing launch to after the last final pass,
+             max over ranks); K jobs are submitted back to back, nothing to stage in HBM
              (the path has no input arrays: a path is a pure function of (seed, path id)).
-  e2e      : the same metric through the public synchronous C-ABI call mcb_price_european
-             (host OptionData in, host mcb_result out, stream sync + D2H inside the timed region).
-  roofline : dominant kernel european_kernel against the SM issue roofline (north_star: "FP32/SFU
+  e2e      : the same metric through the public synchronous C-ABI call mcb_price_european, one call per
+             step (host OptionData in, host mcb_result out through mapped pinned memory); at N > 1 it is
+             rank 0 driving ONE engine over all N GPUs (mcb_engine_create_multi), the other ranks idle.
+  roofline : dominant kernel european_job_kernel against the SM issue roofline (north_star: "FP32/SFU
              compute roofline" -- nothing here touches HBM or tensor cores), algorithmic
              thread-instructions per path from SURVEY.md 8(d); plus `roofline_trajectory`, the
              HBM-bound trajectory-store kernel (configs[2]) against MEASURED_PEAKS.json hbm_gbs.
@@ -38,7 +44,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-METRIC = "GBM paths/sec (European call, 2^30 paths per GPU)"
+METRIC = "GBM paths/sec (European call, 2^30 paths)"
 UNIT = "paths/s"
 PATHS_PER_GPU = 1 << 30
 CFG = dict(S0=100.0, K=100.0, r=0.05, v=0.2, T=1.0)
@@ -46,6 +52,9 @@ SEED = 1234
 
 # Algorithmic work per unit (restated in DESIGN.md "Rooflines")
 INSTR_PER_EUROPEAN_PATH = 57          # 42 INT + 11 FP32 + 4 MUFU thread-instructions, canonical keying
+EXECUTED_INSTR_PER_EUROPEAN_PATH = 52.3   # what the shipped SASS executes per path (ncu, profiles/)
+IMAD_WIDE_PER_CLK_PER_SM = 26.7       # measured, profiles/pipe_microbench_r1.txt
+WALK_IMAD_WIDE_PER_STEP = 4.75        # multi-step walk kernels (bullet, nested): 19 per Philox block of 4 steps
 ISSUE_PER_CLK_PER_SM = 128            # 4 schedulers x 32 lanes
 BYTES_PER_TRAJECTORY_STEP = 4         # one float stored per path-step
 TRAJ_PATHS, TRAJ_STEPS = 1 << 20, 252
@@ -252,9 +261,11 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "European call S0=100 K=100 r=0.05 sigma=0.2 T=1, single step, CPU "
-                               "simulateOptionPriceCPU (inc/tool.cuh:104-130), bounded sample", **CFG},
+                               "simulateOptionPriceCPU (inc/tool.cuh:104-130): a bounded SAMPLE of the 2^30-path "
+                               f"workload per step ({paths} paths; the rate metric does not depend on the sample size)",
+                   "paths_per_step": paths, "full_workload_paths": PATHS_PER_GPU, **CFG},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample,
                          "value_1core": rate1},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -265,6 +276,10 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------------- own arm
+def hexbits(x: float) -> str:
+    return float(x).hex()
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -285,14 +300,17 @@ def run_b200(args):
     sys.stdout.flush()
     json_fd = os.dup(1)
     os.dup2(2, 1)
+    cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        cpu_group = dist.new_group(backend="gloo")     # host-side barriers that keep the GPUs idle
 
     pkg = entry.load_package()
     import importlib
     sharded = importlib.import_module(entry.PKG_NAME + ".sharded")
     eng = pkg.Engine(local)
     pricer = sharded.ShardedPricer(eng, transport=args.transport)
+    transport = pricer.transport
     hbm_gbs, sm_max_mhz, peak_src = measured_peaks()
 
     strong = args.scaling == "strong"
@@ -314,72 +332,122 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def gather_over_ranks(x):
+        if world == 1:
+            return [x]
+        t = torch.zeros(world, dtype=torch.float64, device="cuda")
+        t[rank] = x
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return [float(v) for v in t.tolist()]
+
+    def timed_jobs(n_paths, steps):
+        """Device time (ms, max over ranks) of `steps` jobs of n_paths submitted back to back."""
+        if transport == "peer":
+            barrier()
+            eng.pipeline_timer_start()
+            for _ in range(steps):
+                pricer.european_async(opt, n_paths, SEED, pkg.CALL)
+            ms = eng.pipeline_timer_stop()
+        else:
+            # NCCL transport: kernels, the all-reduce and the events all on ONE torch stream
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                pricer.european_async(opt, n_paths, SEED, pkg.CALL)
+            e1.record()
+            torch.cuda.current_stream().synchronize()
+            ms = float(e0.elapsed_time(e1))
+        barrier()
+        return max_over_ranks(ms)
+
     # ---- device-timed leg -------------------------------------------------------------
-    # everything is enqueued on ONE real stream (the C-ABI reads NULL as "engine stream", and
-    # torch.cuda.Event only sees torch's current stream): kernels, the NCCL allreduce, the events.
     torch.cuda.set_stream(pricer.stream)
     sampler.phase = "warmup"
-    for _ in range(max(args.warmup, 3)):
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         pricer.european_async(opt, n_total, SEED, pkg.CALL)
+    pricer.european_result()
     barrier()
     eng.timing_read(pkg.KERNEL_EUROPEAN)
     eng.timing_enable(True)
     launches0 = eng.launch_count
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler.phase = "timed"
-    ev0.record()
-    for _ in range(args.steps):
-        pricer.european_async(opt, n_total, SEED, pkg.CALL)
-    ev1.record()
-    barrier()
+    ms_total = timed_jobs(n_total, args.steps)
     sampler.phase = "post"
-    ms_total = max_over_ranks(float(ev0.elapsed_time(ev1)))
     launches = eng.launch_count - launches0
     eng.timing_enable(False)
     kern_ms, kern_n = eng.timing_read(pkg.KERNEL_EUROPEAN)
-    result = pricer._fetch(1)[0]
+    result = pricer.european_result()
+    assert result.n_paths == n_total
     assert 0.2 < kern_ms / max(ms_total, 1e-9) <= 1.0 + 1e-3 and kern_n == args.steps, \
         f"kernel events ({kern_ms:.3f} ms / {kern_n}) do not fit inside the timed region ({ms_total:.3f} ms)"
     value = n_total * args.steps / (ms_total * 1e-3)
+    rank_kernel_ms = gather_over_ranks(kern_ms / max(kern_n, 1))
 
-    # ---- end-to-end leg: the public synchronous call, host in / host out ----------------
-    sampler.phase = "e2e"
-    call = (lambda: pricer.price_european(opt, n_total, SEED, pkg.CALL)) if world > 1 else \
-        (lambda: eng.price_european(opt, n_total, SEED, pkg.CALL))
-    for _ in range(3):
-        call()
+    # one job at a time (submit, wait for the result, submit the next): what a latency-bound caller sees
+    sampler.phase = "latency"
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        e2e_res = call()
-    torch.cuda.synchronize()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    e2e_value = n_total * args.steps / e2e_s
-    # bytes: OptionData + Philox round keys travel as kernel parameters; the result (40 B) and the
-    # 64 double segments (1 KiB, kept for mcb_last_segments) come back
-    h2d = 48 + 80
-    d2h = 40 + (0 if world > 1 else 1024)
+        pricer.price_european(opt, n_total, SEED, pkg.CALL)
+    single_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
+
+    # ---- end-to-end leg: the public synchronous C-ABI call, host in / host out ----------------
+    # N = 1: this engine.  N > 1: rank 0 drives ONE engine over all N GPUs (mcb_engine_create_multi,
+    # the route a C caller of wrapper_gpu_option_vanilla takes); the other ranks wait on the CPU.
+    sampler.phase = "e2e"
+    barrier()
+    e2e_value = e2e_s = None
+    e2e_res = None
+    if rank == 0:
+        e2e_eng = eng if world == 1 else pkg.Engine(list(range(world)))
+        for _ in range(3):
+            e2e_eng.price_european(opt, n_total, SEED, pkg.CALL)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_res = e2e_eng.price_european(opt, n_total, SEED, pkg.CALL)
+        e2e_s = time.perf_counter() - t0
+        e2e_value = n_total * args.steps / e2e_s
+        if world > 1:
+            e2e_eng.close()
+    if world > 1:
+        dist.barrier(group=cpu_group)
+    # bytes: OptionData + Philox round keys + job arguments travel as kernel parameters (once per shard);
+    # the result (40 B + its sequence word) and the 64 double segments (1 KiB, kept for
+    # mcb_last_segments) come back through mapped pinned memory
+    h2d = (48 + 80) * world
+    d2h = 48 + 1024
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        "warmup": warm, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
         "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"European call S0=100 K=100 r=0.05 sigma=0.2 T=1, single step, "
-                               f"{'2^30 paths in total' if strong else '2^30 paths per GPU'} "
-                               f"({n_total} paths total), seed {SEED}, Philox4x32-10 keyed by (seed, path id)",
-                   "paths_per_gpu": n_total // world,
-                   "parallelism": f"path-index shards x{world}, " + ("one NCCL allreduce of 1 KiB" if args.transport == "nccl"
-                                                                      else "segments all-gathered by NVLink peer stores"),
+                               f"{'ONE job of 2^30 paths sharded over the GPUs' if strong else '2^30 paths per GPU'} "
+                               f"({n_total} paths per step), seed {SEED}, Philox4x32-10 keyed by (seed, path id)",
+                   "paths_per_step": n_total, "paths_per_gpu": n_total // world,
+                   "parallelism": f"path-index shards x{world}, " + (
+                       "one NCCL allreduce of 1 KiB" if transport == "nccl" else
+                       "one pricing launch per GPU that also folds its segments and stores them into every "
+                       "rank's mailbox over NVLink (CUDA IPC), final tree on a second stream"),
+                   "transport": transport, "jobs_in_flight": "up to 4 (back-to-back submits)",
                    "l2": "n/a: the kernel reads no global memory (64 Ki chunk partials of 8 B written per launch)",
                    **CFG},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "api": "mcb_price_european" if world == 1 else "ShardedPricer.price_european",
-                "ms_per_step": 1e3 * e2e_s / args.steps},
         "gpu_launches": int(launches),
         "price": result.price, "std_error": result.std_error, "closed_form": bs_call(**CFG),
         "z_score": (result.price - bs_call(**CFG)) / result.std_error,
-        "e2e_price_bits_equal": bool(e2e_res.sum == result.sum and e2e_res.sumsq == result.sumsq),
+        "price_hex": hexbits(result.price), "sum_hex": hexbits(result.sum), "sumsq_hex": hexbits(result.sumsq),
+        "single_job_latency": {"ms": single_ms, "paths_per_s": n_total / (single_ms * 1e-3),
+                               "what": "submit one job, wait for its result on the host, then the next"},
+        "rank_kernel_ms": rank_kernel_ms,
     }
+    if rank == 0:
+        line["e2e"] = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                       "api": "mcb_price_european" + ("" if world == 1 else f" on mcb_engine_create_multi({world} GPUs), rank 0"),
+                       "ms_per_step": 1e3 * e2e_s / args.steps}
+        line["e2e_price_bits_equal"] = bool(e2e_res.sum == result.sum and e2e_res.sumsq == result.sumsq
+                                            and e2e_res.price == result.price)
     if kern_n:
         per_launch_s = kern_ms * 1e-3 / kern_n
         paths_per_launch = n_total / world  # this rank's shard
@@ -387,42 +455,52 @@ def run_b200(args):
         sms = eng.device_info().sm_count
         peak = sms * ISSUE_PER_CLK_PER_SM * sm_max_mhz * 1e6 / 1e12
         line["roofline"] = {
-            "bound": "issue", "kernel": "european_kernel", "achieved": achieved, "peak": peak, "unit": "Tinstr/s",
-            "frac": achieved / peak, "traffic": ncu_traffic("european_kernel"),
-            "traffic_note": "DRAM bytes per launch from ncu --set full (profiles/r1_ncu_traffic.json); the kernel "
+            "bound": "issue", "kernel": "european_job_kernel", "achieved": achieved, "peak": peak, "unit": "Tinstr/s",
+            "frac": achieved / peak, "traffic": ncu_traffic("european_job_kernel"),
+            "traffic_note": "DRAM bytes per launch from ncu --set full (profiles/*_ncu_traffic.json); the kernel "
                             "reads no global memory, algorithmic bytes = 512 KiB of chunk partials (stay in L2)",
             "per_unit": f"{INSTR_PER_EUROPEAN_PATH} thread-instr/path (SURVEY 8(d))",
+            "frac_executed": EXECUTED_INSTR_PER_EUROPEAN_PATH / INSTR_PER_EUROPEAN_PATH * achieved / peak,
+            "per_unit_executed": f"{EXECUTED_INSTR_PER_EUROPEAN_PATH} thread-instr/path executed by the SASS (ncu)",
             "peak_how": f"{sms} SMs x {ISSUE_PER_CLK_PER_SM} thread-instr/clk x {sm_max_mhz:.0f} MHz ({peak_src} sm_max_mhz)",
             "kernel_ms": 1e3 * per_launch_s, "kernel_launches": kern_n,
             "kernel_paths_per_s": paths_per_launch / per_launch_s,
             "kernel_share_of_step": kern_ms / kern_n / (ms_total / args.steps),
         }
 
-    # ---- BASELINE configs[4] across the ranks (N > 1): the 1024-set x 2^26-path sweep sharded by path
-    #      index, ONE all-reduce of the 1 MiB segment block, prices bit-identical to the 1-GPU job ----
+    # ---- N > 1 extras: the other scaling mode, and BASELINE configs[4] across the ranks ----
     if world > 1 and not args.headline_only:
         sampler.phase = "extra"
+        other_n = PATHS_PER_GPU * world if strong else PATHS_PER_GPU
+        for _ in range(2):
+            pricer.european_async(opt, other_n, SEED, pkg.CALL)
+        ms_other = timed_jobs(other_n, max(3, args.steps // 2))
+        res_other = pricer.european_result()
+        line["other_workloads"] = {("weak" if strong else "strong") + "_scaling_european": {
+            "paths_per_step": other_n, "paths_per_s": other_n * max(3, args.steps // 2) / (ms_other * 1e-3),
+            "ms_per_step": ms_other / max(3, args.steps // 2), "price": res_other.price,
+            "std_error": res_other.std_error}}
         import numpy as np
         K, V = np.meshgrid(np.linspace(60, 140, 32, dtype=np.float32), np.linspace(0.05, 0.8, 32, dtype=np.float32),
                            indexing="ij")
         k, v = K.ravel().copy(), V.ravel().copy()
-        nccl_pricer = pricer if args.transport == "nccl" else sharded.ShardedPricer(eng, max_sets=1024)
         for _ in range(2):
-            nccl_pricer.sweep_async(opt, k, v, 1 << 26, SEED, pkg.CALL)
+            pricer.sweep_async(opt, k, v, 1 << 26, SEED, pkg.CALL)
         barrier()
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         reps = 5
         s0.record()
         for _ in range(reps):
-            nccl_pricer.sweep_async(opt, k, v, 1 << 26, SEED, pkg.CALL)
+            pricer.sweep_async(opt, k, v, 1 << 26, SEED, pkg.CALL)
         s1.record()
         barrier()
         t_sweep = max_over_ranks(float(s0.elapsed_time(s1))) * 1e-3 / reps
-        res = nccl_pricer._fetch(1024)
-        line["other_workloads"] = {"sweep_1024x2^26_sharded": {
+        res = pricer._fetch(1024)
+        line["other_workloads"]["sweep_1024x2^26_sharded"] = {
             "path_params_per_s": 1024 * (1 << 26) / t_sweep, "ms": 1e3 * t_sweep, "scaling": "strong",
             "collective": "one NCCL all-reduce of 1024 x 64 x 2 doubles (1 MiB)",
-            "price_K100_v0.2ish": res[16 * 32 + 6].price, "bound_per_gpu": "XU: 4.65e12 (path.set)/s"}}
+            "price_K100_v0.2ish": res[16 * 32 + 6].price, "price_hex": hexbits(res[16 * 32 + 6].price),
+            "bound_per_gpu": "XU: 4.65e12 (path.set)/s"}
 
     # ---- other configs of BASELINE.json (rank 0, N = 1 only): bounded, each device-timed ----
     if world == 1 and not args.headline_only:
@@ -450,6 +528,9 @@ def run_b200(args):
             "value": rate, "unit": UNIT, "cores": threads, "kind": kind,
             "sample": f"{threads} threads x {per_thread} paths ({dt:.1f} s) of the 2^30-path workload, "
                       f"calls of 2^20 paths", "value_1core": rate1, "price": price,
+            "gpu_over_cpu": {"e2e_over_all_cores": e2e_value / rate, "e2e_over_1_core": e2e_value / rate1,
+                             "note": "the all-core figure floats with the box's core count; the 1-core figure "
+                                     "is the reference as shipped (single-threaded)"},
         }
         bullet_cpu = reference_bullet_rate(threads)
         if bullet_cpu:
@@ -488,17 +569,19 @@ def other_workloads(torch, pkg, eng, hbm_gbs, peak_src):
         torch.cuda.synchronize()
         return a.elapsed_time(b) * 1e-3 / reps
 
-    # configs[0]: 1e6 paths through the synchronous public call (host in / host out): call latency
-    o0 = pkg.option(N_PATHS=1_000_000, **CFG)
-    for _ in range(5):
-        r0 = eng.price_european(o0, 0, SEED, pkg.CALL)
-    t0 = time.perf_counter()
-    for _ in range(200):
-        r0 = eng.price_european(o0, 0, SEED, pkg.CALL)
-    dt0 = (time.perf_counter() - t0) / 200
-    out["european_1e6_sync_call"] = {"us_per_call": 1e6 * dt0, "paths_per_s": 1e6 / dt0, "price": r0.price,
-                                     "std_error": r0.std_error, "closed_form": bs_call(**CFG),
-                                     "z_score": (r0.price - bs_call(**CFG)) / r0.std_error}
+    # configs[0]: 1e6 paths (and hello.cu's own 1e5, hello.cu:13) through the synchronous public call
+    # (host in / host out): call latency.  ONE launch, result through mapped pinned memory.
+    for label, npaths in (("european_1e6_sync_call", 1_000_000), ("european_1e5_sync_call_hello_cu_size", 100_000)):
+        o0 = pkg.option(N_PATHS=npaths, **CFG)
+        for _ in range(20):
+            r0 = eng.price_european(o0, 0, SEED, pkg.CALL)
+        t0 = time.perf_counter()
+        for _ in range(500):
+            r0 = eng.price_european(o0, 0, SEED, pkg.CALL)
+        dt0 = (time.perf_counter() - t0) / 500
+        out[label] = {"us_per_call": 1e6 * dt0, "paths_per_s": npaths / dt0, "price": r0.price,
+                      "std_error": r0.std_error, "closed_form": bs_call(**CFG),
+                      "z_score": (r0.price - bs_call(**CFG)) / r0.std_error, "launches_per_call": 1}
 
     # configs[2]: 2^20 paths x 252 steps stored path-major to HBM (1.06 GB per launch > 126 MB L2)
     opt = pkg.option(N_STEPS=TRAJ_STEPS, N_PATHS=TRAJ_PATHS, B=120.0, **CFG)
@@ -558,9 +641,11 @@ def other_workloads(torch, pkg, eng, hbm_gbs, peak_src):
     ob = pkg.option(N_STEPS=100, N_PATHS=1 << 24, B=120.0, P1=10, P2=50, **CFG)
     seg = torch.zeros(2 * pkg.SEGMENTS, dtype=torch.float64, device="cuda")
     t = timed(lambda: eng.bullet_segments_async(ob, 1 << 24, SEED, 0, 0.0, 0, 0, 1, seg.data_ptr(), stream), 10)
-    walk_bound = 148 * 30.0 * 1.965e9 / 4.75   # fmaheavy: ~4.75 IMAD.WIDE per step at ~30 /clk/SM (measured)
+    # fmaheavy: IMAD.WIDE per path-step at the measured 26.7 /clk/SM (profiles/pipe_microbench_r1.txt)
+    walk_bound = 148 * IMAD_WIDE_PER_CLK_PER_SM * 1.965e9 / WALK_IMAD_WIDE_PER_STEP
     out["bullet_2^24x100"] = {"path_steps_per_s": (1 << 24) * 100 / t, "ms": 1e3 * t,
-                              "bound": "fmaheavy: 4.75 IMAD.WIDE per path-step at 30/clk/SM (measured) = 1.84e12 /s",
+                              "bound": f"fmaheavy: {WALK_IMAD_WIDE_PER_STEP} IMAD.WIDE per path-step at "
+                                       f"{IMAD_WIDE_PER_CLK_PER_SM}/clk/SM (measured) = {walk_bound:.3g} /s",
                               "frac": (1 << 24) * 100 / t / walk_bound,
                               "frac_of_issue_bound_2.0e12": (1 << 24) * 100 / t / 2.0e12}
 
@@ -603,11 +688,13 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                    help="weak (default): 2^30 paths per GPU; strong: 2^30 paths in total")
-    ap.add_argument("--transport", default="nccl", choices=["nccl", "peer", "fused"],
-                    help="N > 1: how the 64 partial-sum segments cross GPUs: one NCCL all-reduce (default) or direct "
-                         "NVLink stores into CUDA-IPC peer mailboxes from inside the segment pass")
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
+                    help="strong (default, BASELINE.json's metric): ONE 2^30-path job sharded over the GPUs; "
+                         "weak: 2^30 paths per GPU")
+    ap.add_argument("--transport", default="auto", choices=["auto", "nccl", "peer"],
+                    help="N > 1: how the 64 partial-sum segments cross GPUs: direct NVLink stores into CUDA-IPC peer "
+                         "mailboxes from inside the pricing kernel (peer), one NCCL all-reduce (nccl), or peer when "
+                         "CUDA IPC connects on every rank and NCCL otherwise (auto, default); same bits either way")
     ap.add_argument("--headline-only", action="store_true", help="skip the other BASELINE configs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

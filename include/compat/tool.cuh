@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <iostream>
 #include <random>
+#include <string>
 
 #include <cuda_runtime.h>
 
@@ -62,14 +63,42 @@ inline void mcb_compat_test_cuda(cudaError_t error, const char *file, int line)
 }
 #define testCUDA(error) (mcb_compat_test_cuda(error, __FILE__, __LINE__))
 
-// One process-wide engine on device 0 (the reference always runs on the implicit device 0).
+// One process-wide engine.  The reference always runs on the implicit device 0 (inc/wrappers.cuh:33-57);
+// so does this shim by default.  MCB200_DEVICES opts the SAME unmodified caller (hello.cu, testing.cu) into
+// every GPU of the box -- "all", a count ("8") or a device list ("0,1,2,3") -- through
+// mcb_engine_create_multi: the wrappers then shard internally and return the same bits.
 inline mcb_engine *mcb_compat_engine()
 {
     static mcb_engine *engine = nullptr;
     static bool tried = false;
     if (!tried) {
         tried = true;
-        if (mcb_engine_create(0, &engine) != MCB_OK) engine = nullptr;  // message stays in mcb_last_error()
+        int devices[MCB_MAX_PEERS] = {0};
+        int n = 1;
+        if (const char *env = getenv("MCB200_DEVICES")) {
+            int count = 0;
+            cudaGetDeviceCount(&count);
+            const std::string spec(env);
+            if (spec == "all") {
+                n = count;
+            } else if (spec.find(',') == std::string::npos) {
+                n = atoi(env);
+            } else {
+                n = 0;
+                size_t pos = 0;
+                while (pos <= spec.size() && n < MCB_MAX_PEERS) {
+                    const size_t comma = spec.find(',', pos);
+                    devices[n++] = atoi(spec.substr(pos, comma == std::string::npos ? comma : comma - pos).c_str());
+                    if (comma == std::string::npos) break;
+                    pos = comma + 1;
+                }
+            }
+            if (n < 1) n = 1;
+            if (n > MCB_MAX_PEERS) n = MCB_MAX_PEERS;
+            if (spec.find(',') == std::string::npos)
+                for (int i = 0; i < n; ++i) devices[i] = i;
+        }
+        if (mcb_engine_create_multi(devices, n, &engine) != MCB_OK) engine = nullptr;  // message stays in mcb_last_error()
     }
     return engine;
 }

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define MCB_VERSION 1
+#define MCB_VERSION 2
 
 /* Geometry of the deterministic reduction (replaces inc/reduce.cuh + the float atomics). */
 #define MCB_SLOTS 256                   /* accumulation slots per chunk = CTA threads          */
@@ -67,7 +67,8 @@ typedef enum mcb_status {
     MCB_ERR_INVALID = 1,   /* bad argument                                  */
     MCB_ERR_CUDA = 2,      /* CUDA runtime error (see mcb_last_error)       */
     MCB_ERR_NO_DEVICE = 3, /* no usable sm_100 device                       */
-    MCB_ERR_NOMEM = 4
+    MCB_ERR_NOMEM = 4,
+    MCB_ERR_TIMEOUT = 5    /* a peer shard never delivered (result poisoned with NaN) */
 } mcb_status;
 
 enum { MCB_CALL = 0, MCB_PUT = 1 };
@@ -80,6 +81,17 @@ typedef struct mcb_engine mcb_engine;
 /* ---- engine lifetime.  Replaces the per-call cudaMalloc/cudaFree of every wrapper
  *      (inc/wrappers.cuh:38-55) with a persistent handle owning stream + workspaces. ---- */
 int mcb_engine_create(int device, mcb_engine **out);
+/* ONE engine over several GPUs of this process (SURVEY.md 8(b) "multi-GPU handled inside the
+ * engine", 8(e)): devices[0] leads.  Every whole-job call below then shards internally by path
+ * index -- European / bullet / sweep by reduction segments (the (sum, sumsq) segments cross NVLink as
+ * plain peer stores from inside the kernels; no collective library), trajectories and nested MC by
+ * contiguous path slabs (host destinations) -- and returns the SAME bits as a single-device engine.
+ * The reference is single-GPU (inc/wrappers.cuh:33-57 runs on the implicit device 0); a caller of
+ * wrapper_gpu_option_vanilla gets all GPUs by creating its engine here.  A device may be listed
+ * more than once (several shards on one GPU: used by the single-GPU tests of the sharded path).
+ * Buffers passed with MCB_DEVICE must live on devices[0]; such calls run on the leader alone. */
+int mcb_engine_create_multi(const int *devices, int n_devices, mcb_engine **out);
+int mcb_engine_shard_count(mcb_engine *e);
 int mcb_engine_destroy(mcb_engine *e);
 const char *mcb_last_error(void);
 int mcb_version(void);
@@ -182,31 +194,48 @@ int mcb_nested_async(mcb_engine *e, const mcb_option_data *opt, uint64_t first_o
                      uint64_t seed_outer, uint64_t seed_inner, int discount_mode, float *d_F,
                      float *d_prices, int *d_counts, void *stream);
 
-/* ---- NCCL-free exchange over NVLink peer memory (optional; no reference counterpart) --------
- * The only data that crosses GPUs is the 64 (sum, sumsq) segments (1 KiB).  Instead of handing
- * them to a collective library, the segment pass of rank g can STORE the segments it owns straight
- * into every peer's mailbox (st.global on CUDA-IPC-mapped peer memory, NVLink / NVSwitch), publish
- * an epoch flag, and the final pass of every rank waits (bounded spin on its OWN memory) for the G
- * flags before running the fixed tree: compute + all-gather in two launches, bit-identical to the
- * single-GPU result.  One process per GPU:
- *   mcb_peer_mailbox_create   allocates this rank's mailbox, returns its 64-byte cudaIpcMemHandle;
- *   (the caller all-gathers the handles, e.g. torch.distributed.all_gather_object)
- *   mcb_peer_mailbox_connect  maps every peer's mailbox;
- *   mcb_european_peer_async   european chunks -> peer-storing segment pass -> waiting final pass,
- *                             all enqueued on `stream`; d_results receives one mcb_result.
- * Every rank must issue the same sequence of *_peer_async calls.  The wait is bounded (~seconds):
- * on timeout the result's n_paths is set to 0 instead of hanging. */
+/* ---- the European job pipeline: ONE launch per price, results through mapped host memory --------
+ * mcb_price_european is submit + collect.  A job is priced by the engine's group of shards:
+ *   - a plain engine: one shard.  The pricing kernel's last CTA folds the segments, runs the final
+ *     tree and writes the mcb_result into pinned host memory: one launch, no copy, no stream sync
+ *     (replaces setup_kernel + pricing kernel + cudaDeviceSynchronize + cudaMemcpy + host finalise of
+ *     inc/wrappers.cuh:38-56);
+ *   - a multi-device engine (mcb_engine_create_multi): one shard per listed GPU, one launch each;
+ *   - one engine per PROCESS (one process per GPU, e.g. under torchrun), connected with
+ *     mcb_peer_mailbox_create / _connect below: rank g's kernel stores the segments it owns into
+ *     every rank's mailbox over NVLink (CUDA-IPC mapped peer memory) and publishes an epoch flag.
+ * With more than one shard the final tree is a one-warp kernel on the engine's second stream that
+ * waits for the flags (bounded, see mcb_set_wait_timeout_ms), so the pricing stream never waits for a
+ * peer: job e + 1 is priced while job e's segments are still crossing NVLink.  Up to
+ * MCB_PIPELINE_DEPTH jobs may be in flight; the last MCB_RESULT_RING results can be collected.
+ * Results are bit-identical for every group shape.  Every rank of a process group must submit the
+ * same jobs in the same order.  If a peer never delivers, collect returns MCB_ERR_TIMEOUT and the
+ * result is NaN with n_paths = 0 (never a plausible number). */
+#define MCB_PIPELINE_DEPTH 4
+#define MCB_RESULT_RING 8
+int mcb_european_submit(mcb_engine *e, const mcb_option_data *opt, uint64_t n_paths, uint64_t seed,
+                        int option_type, uint64_t *ticket);
+int mcb_european_collect(mcb_engine *e, uint64_t ticket, mcb_result *out);
+/* Device time of a batch of pipelined jobs: start drains every stream and records an event,
+ * stop records one behind everything submitted since (all shards, both streams), waits for it and
+ * returns the elapsed milliseconds (CUDA events on the launching streams). */
+int mcb_pipeline_timer_start(mcb_engine *e);
+int mcb_pipeline_timer_stop(mcb_engine *e, double *elapsed_ms);
+
+/* One engine per process: this rank's mailbox as a 64-byte cudaIpcMemHandle; the caller all-gathers
+ * the handles and the ranks' mcb_peer_epoch values (e.g. torch.distributed.all_gather_object) and
+ * passes all handles plus the MAXIMUM epoch to connect, then runs a barrier before the first
+ * submit.  Any world size up to MCB_MAX_PEERS; at most one rank per GPU (kernels of different
+ * ranks wait for one another). */
 #define MCB_IPC_HANDLE_BYTES 64
 #define MCB_MAX_PEERS 16
 int mcb_peer_mailbox_create(mcb_engine *e, void *handle_out);
-int mcb_peer_mailbox_connect(mcb_engine *e, int rank, int world, const void *all_handles);
-int mcb_european_peer_async(mcb_engine *e, const mcb_option_data *opt, uint64_t n_paths, uint64_t seed,
-                            int option_type, mcb_result *d_results, void *stream);
-/* The same in ONE launch: the pricing kernel's last CTA per segment folds and peer-stores it, the
- * CTA that completes the rank's last segment publishes the flag, waits for the peers and runs the
- * final tree.  Same bits as every other path; jobs of fewer than 64 chunks use the 3-launch form. */
-int mcb_european_fused_peer_async(mcb_engine *e, const mcb_option_data *opt, uint64_t n_paths, uint64_t seed,
-                                  int option_type, mcb_result *d_results, void *stream);
+int mcb_peer_epoch(mcb_engine *e, uint64_t *epoch);
+int mcb_peer_mailbox_connect(mcb_engine *e, int rank, int world, const void *all_handles, uint64_t base_epoch);
+/* Bound of every device-side wait for a peer (default 10 000 ms, measured with %globaltimer) and
+ * the number of waits that ran out so far. */
+int mcb_set_wait_timeout_ms(mcb_engine *e, uint64_t ms);
+int mcb_peer_timeouts(mcb_engine *e, uint64_t *count);
 
 /* Number of kernel launches this engine has issued (bench.py's gpu_launches). */
 uint64_t mcb_launch_count(mcb_engine *e);

@@ -35,7 +35,8 @@ CALL, PUT = 0, 1
 DISCOUNT_COMPAT, DISCOUNT_CORRECT = 0, 1
 HOST, DEVICE = 0, 1
 
-OK, ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_NOMEM = 0, 1, 2, 3, 4
+OK, ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_NOMEM, ERR_TIMEOUT = 0, 1, 2, 3, 4, 5
+PIPELINE_DEPTH, RESULT_RING, MAX_PEERS = 4, 8, 16
 KERNEL_EUROPEAN, KERNEL_BULLET, KERNEL_TRAJECTORY, KERNEL_NESTED, KERNEL_SWEEP = 0, 1, 2, 3, 4
 
 
@@ -89,6 +90,8 @@ _RP = C.POINTER(Result)
 # name -> (restype, argtypes): every symbol include/mcb200.h declares
 SIGNATURES = {
     "mcb_engine_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
+    "mcb_engine_create_multi": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.POINTER(_vp)]),
+    "mcb_engine_shard_count": (C.c_int, [_vp]),
     "mcb_engine_destroy": (C.c_int, [_vp]),
     "mcb_last_error": (C.c_char_p, []),
     "mcb_version": (C.c_int, []),
@@ -113,10 +116,15 @@ SIGNATURES = {
     "mcb_combine_segments_async": (C.c_int, [_vp, _vp, C.c_int, _u64, C.c_float, C.c_float, _vp, _vp]),
     "mcb_trajectories_async": (C.c_int, [_vp, _OP, _u64, _u64, _u64, _vp, _vp, _vp]),
     "mcb_nested_async": (C.c_int, [_vp, _OP, _u64, _u64, _u64, _u64, C.c_int, _vp, _vp, _vp, _vp]),
+    "mcb_european_submit": (C.c_int, [_vp, _OP, _u64, _u64, C.c_int, C.POINTER(_u64)]),
+    "mcb_european_collect": (C.c_int, [_vp, _u64, _RP]),
+    "mcb_pipeline_timer_start": (C.c_int, [_vp]),
+    "mcb_pipeline_timer_stop": (C.c_int, [_vp, C.POINTER(C.c_double)]),
     "mcb_peer_mailbox_create": (C.c_int, [_vp, _vp]),
-    "mcb_peer_mailbox_connect": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
-    "mcb_european_peer_async": (C.c_int, [_vp, _OP, _u64, _u64, C.c_int, _vp, _vp]),
-    "mcb_european_fused_peer_async": (C.c_int, [_vp, _OP, _u64, _u64, C.c_int, _vp, _vp]),
+    "mcb_peer_epoch": (C.c_int, [_vp, C.POINTER(_u64)]),
+    "mcb_peer_mailbox_connect": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _u64]),
+    "mcb_set_wait_timeout_ms": (C.c_int, [_vp, _u64]),
+    "mcb_peer_timeouts": (C.c_int, [_vp, C.POINTER(_u64)]),
     "mcb_launch_count": (_u64, [_vp]),
     "mcb_timing_enable": (C.c_int, [_vp, C.c_int]),
     "mcb_timing_read": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_double), C.POINTER(_u64)]),
@@ -160,15 +168,28 @@ def _np(a, dtype):
 
 
 class Engine:
-    """Persistent handle: stream + workspaces on one GPU (replaces the per-call cudaMalloc /
-    cudaFree of every reference wrapper, inc/wrappers.cuh:38-55)."""
+    """Persistent handle: streams + workspaces on one GPU (replaces the per-call cudaMalloc /
+    cudaFree of every reference wrapper, inc/wrappers.cuh:38-55) -- or, with a list of devices,
+    ONE engine over several GPUs of this process (``mcb_engine_create_multi``): the whole-job calls
+    then shard internally and return the same bits."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device=0):
         self._lib = load_library()
         h = _vp()
-        _check(self._lib.mcb_engine_create(device, C.byref(h)))
+        if isinstance(device, (list, tuple)):
+            devs = (C.c_int * len(device))(*device)
+            _check(self._lib.mcb_engine_create_multi(devs, len(device), C.byref(h)))
+            self.devices = list(device)
+            self.device = self.devices[0]
+        else:
+            _check(self._lib.mcb_engine_create(device, C.byref(h)))
+            self.device = device
+            self.devices = [device]
         self._h = h
-        self.device = device
+
+    @property
+    def shard_count(self) -> int:
+        return int(self._lib.mcb_engine_shard_count(self._h))
 
     def close(self):
         if getattr(self, "_h", None):
@@ -304,21 +325,49 @@ class Engine:
     def combine_segments_async(self, d_segments, n_sets, n_paths, r, T, d_results, stream=None):
         _check(self._lib.mcb_combine_segments_async(self._h, d_segments, n_sets, n_paths, r, T, d_results, stream))
 
-    # ---- NCCL-free exchange over NVLink peer memory ------------------------------------------------
+    # ---- the European job pipeline (one launch per shard, result through mapped host memory) --------
+    def european_submit(self, opt, n_paths=0, seed=1234, option_type=CALL) -> int:
+        t = _u64()
+        _check(self._lib.mcb_european_submit(self._h, C.byref(opt), n_paths, seed, option_type, C.byref(t)))
+        return int(t.value)
+
+    def european_collect(self, ticket) -> Result:
+        out = Result()
+        _check(self._lib.mcb_european_collect(self._h, ticket, C.byref(out)))
+        return out
+
+    def pipeline_timer_start(self):
+        _check(self._lib.mcb_pipeline_timer_start(self._h))
+
+    def pipeline_timer_stop(self) -> float:
+        ms = C.c_double()
+        _check(self._lib.mcb_pipeline_timer_stop(self._h, C.byref(ms)))
+        return ms.value
+
+    # ---- one engine per process: mailboxes mapped over CUDA IPC (NVLink peer stores) ---------------
     def peer_mailbox_create(self) -> bytes:
         buf = C.create_string_buffer(64)
         _check(self._lib.mcb_peer_mailbox_create(self._h, buf))
         return buf.raw
 
-    def peer_mailbox_connect(self, rank, world, handles):
+    def peer_epoch(self) -> int:
+        t = _u64()
+        _check(self._lib.mcb_peer_epoch(self._h, C.byref(t)))
+        return int(t.value)
+
+    def peer_mailbox_connect(self, rank, world, handles, base_epoch):
         blob = b"".join(handles)
         if len(blob) != 64 * world:
             raise ValueError("need one 64-byte handle per rank")
-        _check(self._lib.mcb_peer_mailbox_connect(self._h, rank, world, blob))
+        _check(self._lib.mcb_peer_mailbox_connect(self._h, rank, world, blob, base_epoch))
 
-    def european_peer_async(self, opt, n_paths, seed, option_type, d_results, stream=None, fused=False):
-        fn = self._lib.mcb_european_fused_peer_async if fused else self._lib.mcb_european_peer_async
-        _check(fn(self._h, C.byref(opt), n_paths, seed, option_type, d_results, stream))
+    def set_wait_timeout_ms(self, ms):
+        _check(self._lib.mcb_set_wait_timeout_ms(self._h, int(ms)))
+
+    def peer_timeouts(self) -> int:
+        t = _u64()
+        _check(self._lib.mcb_peer_timeouts(self._h, C.byref(t)))
+        return int(t.value)
 
     # ---- parity hooks ------------------------------------------------------------------------
     def philox_blocks(self, seed, subsequences, blocks, library=False):

@@ -11,7 +11,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <chrono>
 #include <new>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -80,9 +84,12 @@ struct DeviceBuffer {
 
 }  // namespace
 
+constexpr int kHostRing = 8;   // MCB_RESULT_RING: results kept for mcb_european_collect
+
 struct mcb_engine {
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;         // main stream: every pricing / trajectory launch
+    cudaStream_t f_stream = nullptr;       // final passes of world > 1 jobs (never blocks `stream`)
     cudaDeviceProp prop{};
     DeviceBuffer<float2> partials;
     DeviceBuffer<double> segments;
@@ -92,16 +99,26 @@ struct mcb_engine {
     DeviceBuffer<float> traj_ws;           // mcb_simulate_trajectories to a host buffer: one slab of rows (+ counts)
     DeviceBuffer<float4> sweep_sets;       // sweep: (c0, c1, K, -) per parameter set
     std::vector<float4> h_sweep_sets;      // host staging for sweep_sets (pageable on purpose)
-    // peer-memory exchange (mcb_peer_mailbox_*): my mailbox, the peers' mailboxes mapped over CUDA IPC
-    PeerMailbox *mailbox = nullptr;
-    PeerTable peers{};
+    // ---- the job pipeline (mcb_european_submit / collect) ----
+    PeerMailbox *mailbox = nullptr;        // this shard's mailbox (its own HBM)
+    PeerTable peers{};                     // box[r] = shard r's mailbox as addressable from this device
+    unsigned int *seg_tickets = nullptr;   // [kSegments + 1], zero between launches
+    int rank = 0, world = 1;               // this shard's place in its group
+    bool in_process = false;               // group = the shards of ONE multi-device engine (events, no device spins)
+    bool ipc = false;                      // group = one engine per process, mailboxes mapped over CUDA IPC
     void *peer_mapped[kMaxPeers] = {};     // what cudaIpcOpenMemHandle returned (to close on destroy)
-    int peer_rank = -1, peer_world = 0;
-    unsigned long long peer_epoch = 0;
-    DeviceBuffer<unsigned int> seg_tickets; // fused peer kernel: per-segment arrival counters (zero between launches)
+    std::vector<mcb_engine *> shards;      // leader of a multi-device engine: every shard, itself first
+    mcb_engine *leader = nullptr;          // sub-engine of a multi-device engine: its leader
+    unsigned long long job_epoch = 0;      // jobs submitted so far (leader / single engine)
+    unsigned long long timeout_ns = 10ull * 1000000000ull;   // bound of every device-side wait
+    cudaEvent_t p_done[kRing] = {};        // pricing launch of the job in each ring slot has finished (this shard)
+    cudaEvent_t f_done[kRing] = {};        // final pass of the job in each ring slot has finished (leader)
+    cudaEvent_t t_begin = nullptr, t_end = nullptr;   // mcb_pipeline_timer_*
+    HostSlot *h_ring = nullptr;            // mapped pinned: results of the last kHostRing jobs
+    uint64_t h_ring_paths[kHostRing] = {}; // n_paths of the job in each host slot (sanity)
     mcb_result *h_results = nullptr;       // pinned
     size_t h_results_cap = 0;
-    double *h_segments = nullptr;          // pinned, [MCB_SEGMENTS][2] of the last whole-job call
+    double *h_segments = nullptr;          // mapped pinned, [MCB_SEGMENTS][2] of the last whole-job call
     uint64_t launches = 0;
     // optional per-kernel CUDA-event timing (mcb_timing_enable): one (start, stop) pair per
     // hot-path launch, recorded on the launching stream, read back by mcb_timing_read.
@@ -245,10 +262,10 @@ int launch_european(mcb_engine *e, const EuropeanParams &prm, int option_type, u
 }
 
 int launch_segments(mcb_engine *e, const float2 *partials, uint64_t stride, uint64_t first_chunk, uint64_t n_chunks,
-                    int seg_lo, int seg_hi, int n_sets, double *d_segments, cudaStream_t st)
+                    int seg_lo, int seg_hi, int n_sets, double *d_segments, cudaStream_t st, int write_unowned = 1)
 {
     segment_kernel<<<dim3(MCB_SEGMENTS, (unsigned)n_sets), kSlots, 0, st>>>(partials, stride, first_chunk, n_chunks,
-                                                                           seg_lo, seg_hi, d_segments);
+                                                                           seg_lo, seg_hi, write_unowned, d_segments);
     e->launches++;
     CU(cudaGetLastError());
     return MCB_OK;
@@ -356,9 +373,8 @@ extern "C" {
 const char *mcb_last_error(void) { return g_error; }
 int mcb_version(void) { return MCB_VERSION; }
 
-int mcb_engine_create(int device, mcb_engine **out)
+static int engine_create_one(int device, mcb_engine **out)
 {
-    if (!out) return fail(MCB_ERR_INVALID, "out is NULL");
     *out = nullptr;
     int count = 0;
     cudaError_t err = cudaGetDeviceCount(&count);
@@ -383,14 +399,34 @@ int mcb_engine_create(int device, mcb_engine **out)
         return fail(MCB_ERR_NO_DEVICE, "device %d is sm_%d%d; this library carries sm_100a code only", device, major,
                     minor);
     }
+    int prio_lo = 0, prio_hi = 0;
+    if (err == cudaSuccess) err = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
-    if (err == cudaSuccess) err = cudaMallocHost(&e->h_segments, sizeof(double) * (2 * MCB_SEGMENTS + 8));
+    // the final passes are single warps that must not queue behind thousands of pricing CTAs
+    if (err == cudaSuccess) err = cudaStreamCreateWithPriority(&e->f_stream, cudaStreamNonBlocking, prio_hi);
+    if (err == cudaSuccess)
+        err = cudaHostAlloc(&e->h_segments, sizeof(double) * (2 * MCB_SEGMENTS + 8),
+                            cudaHostAllocMapped | cudaHostAllocPortable);
+    if (err == cudaSuccess)
+        err = cudaHostAlloc(&e->h_ring, sizeof(HostSlot) * kHostRing, cudaHostAllocMapped | cudaHostAllocPortable);
+    if (err == cudaSuccess) err = cudaMalloc(&e->mailbox, sizeof(PeerMailbox));
+    if (err == cudaSuccess) err = cudaMemset(e->mailbox, 0, sizeof(PeerMailbox));
+    if (err == cudaSuccess) err = cudaMalloc(&e->seg_tickets, sizeof(unsigned int) * (kSegments + 1));
+    if (err == cudaSuccess) err = cudaMemset(e->seg_tickets, 0, sizeof(unsigned int) * (kSegments + 1));
+    for (int i = 0; i < kRing && err == cudaSuccess; ++i) {
+        err = cudaEventCreateWithFlags(&e->p_done[i], cudaEventDisableTiming);
+        if (err == cudaSuccess) err = cudaEventCreateWithFlags(&e->f_done[i], cudaEventDisableTiming);
+    }
+    if (err == cudaSuccess) err = cudaEventCreate(&e->t_begin);
+    if (err == cudaSuccess) err = cudaEventCreate(&e->t_end);
     if (err != cudaSuccess) {
         int rc = fail(MCB_ERR_CUDA, "engine setup failed: %s", cudaGetErrorString(err));
         mcb_engine_destroy(e);
         return rc;
     }
     memset(e->h_segments, 0, sizeof(double) * (2 * MCB_SEGMENTS + 8));
+    memset(e->h_ring, 0, sizeof(HostSlot) * kHostRing);
+    e->peers.box[0] = e->mailbox;
     if (e->segments.reserve(2 * MCB_SEGMENTS + 8) || reserve_results(e, 1)) {
         mcb_engine_destroy(e);
         return MCB_ERR_NOMEM;
@@ -399,19 +435,95 @@ int mcb_engine_create(int device, mcb_engine **out)
     return MCB_OK;
 }
 
+int mcb_engine_create(int device, mcb_engine **out)
+{
+    if (!out) return fail(MCB_ERR_INVALID, "out is NULL");
+    return engine_create_one(device, out);
+}
+
+int mcb_engine_create_multi(const int *devices, int n_devices, mcb_engine **out)
+{
+    if (!out) return fail(MCB_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (!devices || n_devices < 1 || n_devices > kMaxPeers)
+        return fail(MCB_ERR_INVALID, "need 1..%d devices", kMaxPeers);
+    std::vector<mcb_engine *> shards;
+    int rc = MCB_OK;
+    for (int i = 0; i < n_devices && rc == MCB_OK; ++i) {
+        mcb_engine *s = nullptr;
+        rc = engine_create_one(devices[i], &s);
+        if (rc == MCB_OK) shards.push_back(s);
+    }
+    // every shard stores into the leader's mailbox / segment buffer: peer access both ways
+    for (size_t i = 0; i < shards.size() && rc == MCB_OK; ++i)
+        for (size_t j = 0; j < shards.size() && rc == MCB_OK; ++j) {
+            const int a = shards[i]->device, b = shards[j]->device;
+            if (a == b) continue;
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, a, b);
+            if (!can) {
+                rc = fail(MCB_ERR_CUDA, "device %d cannot access device %d over NVLink/PCIe peer memory", a, b);
+                break;
+            }
+            DeviceGuard g(a);
+            cudaError_t err = cudaDeviceEnablePeerAccess(b, 0);
+            if (err == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+            else if (err != cudaSuccess) rc = fail(MCB_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d -> %d): %s", a, b,
+                                                   cudaGetErrorString(err));
+        }
+    if (rc != MCB_OK) {
+        const std::string msg = g_error;   // the destructors below must not clobber the message
+        for (mcb_engine *s : shards) mcb_engine_destroy(s);
+        snprintf(g_error, sizeof(g_error), "%s", msg.c_str());
+        return rc;
+    }
+    mcb_engine *L = shards[0];
+    if (shards.size() > 1) {
+        for (size_t i = 0; i < shards.size(); ++i) {
+            mcb_engine *s = shards[i];
+            s->rank = (int)i;
+            s->world = (int)shards.size();
+            s->in_process = true;
+            s->leader = i ? L : nullptr;
+            for (size_t r = 0; r < shards.size(); ++r) s->peers.box[r] = shards[r]->mailbox;
+        }
+        L->shards = shards;
+    }
+    *out = L;
+    return MCB_OK;
+}
+
+int mcb_engine_shard_count(mcb_engine *e) { return e ? (e->shards.empty() ? 1 : (int)e->shards.size()) : 0; }
+
 int mcb_engine_destroy(mcb_engine *e)
 {
     if (!e) return MCB_OK;
+    if (!e->shards.empty()) {            // leader: the other shards go first (their stores target this one)
+        std::vector<mcb_engine *> subs(e->shards.begin() + 1, e->shards.end());
+        e->shards.clear();
+        for (mcb_engine *s : subs) {
+            s->leader = nullptr;
+            mcb_engine_destroy(s);
+        }
+    }
     DeviceGuard g(e->device);
     if (e->stream) {
         cudaStreamSynchronize(e->stream);
+        if (e->f_stream) cudaStreamSynchronize(e->f_stream);
         cudaStreamDestroy(e->stream);
     }
+    if (e->f_stream) cudaStreamDestroy(e->f_stream);
     for (auto *v : {&e->timed, &e->event_pool})
         for (auto &t : *v) {
             cudaEventDestroy(t.start);
             cudaEventDestroy(t.stop);
         }
+    for (int i = 0; i < kRing; ++i) {
+        if (e->p_done[i]) cudaEventDestroy(e->p_done[i]);
+        if (e->f_done[i]) cudaEventDestroy(e->f_done[i]);
+    }
+    if (e->t_begin) cudaEventDestroy(e->t_begin);
+    if (e->t_end) cudaEventDestroy(e->t_end);
     e->partials.release();
     e->segments.release();
     e->results.release();
@@ -422,9 +534,11 @@ int mcb_engine_destroy(mcb_engine *e)
     for (int r = 0; r < kMaxPeers; ++r)
         if (e->peer_mapped[r]) cudaIpcCloseMemHandle(e->peer_mapped[r]);
     if (e->mailbox) cudaFree(e->mailbox);
-    e->seg_tickets.release();
+    if (e->seg_tickets) cudaFree(e->seg_tickets);
     if (e->h_results) cudaFreeHost(e->h_results);
     if (e->h_segments) cudaFreeHost(e->h_segments);
+    if (e->h_ring) cudaFreeHost(e->h_ring);
+    cudaGetLastError();
     delete e;
     return MCB_OK;
 }
@@ -444,146 +558,310 @@ int mcb_get_device_info(mcb_engine *e, mcb_device_info *out)
     return MCB_OK;
 }
 
+static int sync_all(mcb_engine *e)
+{
+    const size_t n = e->shards.empty() ? 1 : e->shards.size();
+    for (size_t i = 0; i < n; ++i) {
+        mcb_engine *s = e->shards.empty() ? e : e->shards[i];
+        DeviceGuard g(s->device);
+        CU(cudaStreamSynchronize(s->stream));
+        CU(cudaStreamSynchronize(s->f_stream));
+    }
+    return MCB_OK;
+}
+
 int mcb_synchronize(mcb_engine *e)
 {
     if (!e) return fail(MCB_ERR_INVALID, "engine is NULL");
-    DeviceGuard g(e->device);
-    CU(cudaStreamSynchronize(e->stream));
-    return MCB_OK;
+    return sync_all(e);
 }
 
 // --------------------------------------------------------------- peer-memory exchange (NVLink)
 static_assert(MCB_MAX_PEERS == kMaxPeers && MCB_IPC_HANDLE_BYTES == sizeof(cudaIpcMemHandle_t), "peer ABI");
+static_assert(MCB_PIPELINE_DEPTH == kRing && MCB_RESULT_RING == kHostRing, "pipeline ABI");
+static_assert(sizeof(HostSlot) == 64, "one result slot per 64-byte line");
 
 int mcb_peer_mailbox_create(mcb_engine *e, void *handle_out)
 {
     if (!e || !handle_out) return fail(MCB_ERR_INVALID, "NULL argument");
+    if (e->in_process || e->leader) return fail(MCB_ERR_INVALID, "a multi-device engine is its own group");
     DeviceGuard g(e->device);
-    if (!e->mailbox) {
-        CU(cudaMalloc(&e->mailbox, sizeof(PeerMailbox)));
-        CU(cudaMemset(e->mailbox, 0, sizeof(PeerMailbox)));
-    }
     cudaIpcMemHandle_t h;
     CU(cudaIpcGetMemHandle(&h, e->mailbox));
     memcpy(handle_out, &h, sizeof(h));
     return MCB_OK;
 }
 
-int mcb_peer_mailbox_connect(mcb_engine *e, int rank, int world, const void *all_handles)
+int mcb_peer_epoch(mcb_engine *e, uint64_t *epoch)
+{
+    if (!e || !epoch) return fail(MCB_ERR_INVALID, "NULL argument");
+    *epoch = e->job_epoch;
+    return MCB_OK;
+}
+
+int mcb_peer_mailbox_connect(mcb_engine *e, int rank, int world, const void *all_handles, uint64_t base_epoch)
 {
     if (!e || !all_handles) return fail(MCB_ERR_INVALID, "NULL argument");
-    if (!e->mailbox) return fail(MCB_ERR_INVALID, "call mcb_peer_mailbox_create first");
+    if (e->in_process || e->leader) return fail(MCB_ERR_INVALID, "a multi-device engine is its own group");
     if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world)
         return fail(MCB_ERR_INVALID, "bad rank/world %d/%d (at most %d peers)", rank, world, kMaxPeers);
-    if (MCB_SEGMENTS % world != 0) return fail(MCB_ERR_INVALID, "world must divide %d", MCB_SEGMENTS);
+    if (base_epoch < e->job_epoch)
+        return fail(MCB_ERR_INVALID, "base_epoch %llu is behind this engine's %llu: pass the maximum over all ranks",
+                    (unsigned long long)base_epoch, e->job_epoch);
     DeviceGuard g(e->device);
+    CU(cudaStreamSynchronize(e->stream));
+    CU(cudaStreamSynchronize(e->f_stream));
     const cudaIpcMemHandle_t *h = static_cast<const cudaIpcMemHandle_t *>(all_handles);
+    for (int r = 0; r < kMaxPeers; ++r) {
+        if (e->peer_mapped[r]) {
+            cudaIpcCloseMemHandle(e->peer_mapped[r]);
+            e->peer_mapped[r] = nullptr;
+        }
+        e->peers.box[r] = nullptr;
+    }
     for (int r = 0; r < world; ++r) {
         if (r == rank) {
             e->peers.box[r] = e->mailbox;
             continue;
-        }
-        if (e->peer_mapped[r]) {
-            cudaIpcCloseMemHandle(e->peer_mapped[r]);
-            e->peer_mapped[r] = nullptr;
         }
         void *p = nullptr;
         CU(cudaIpcOpenMemHandle(&p, h[r], cudaIpcMemLazyEnablePeerAccess));
         e->peer_mapped[r] = p;
         e->peers.box[r] = static_cast<PeerMailbox *>(p);
     }
-    e->peer_rank = rank;
-    e->peer_world = world;
-    // peer_epoch is NOT reset: the mailbox (and the epochs already published in it) outlives a
-    // re-connect, and the flags are compared with "<", so epochs must stay monotonic per engine
+    // Every rank starts the group's jobs at the SAME epoch (the caller all-gathers mcb_peer_epoch and
+    // passes the maximum): flags and acks left by earlier groups are <= base_epoch, so they can
+    // neither satisfy a wait of a new job nor hold a producer back.  My own mailbox is reset here;
+    // the caller's barrier after connect orders this before any peer's first store.
+    std::vector<unsigned long long> acks(kMaxPeers, (unsigned long long)base_epoch);
+    CU(cudaMemcpy(e->mailbox->consumed, acks.data(), sizeof(unsigned long long) * kMaxPeers, cudaMemcpyHostToDevice));
+    e->job_epoch = base_epoch;
+    e->rank = rank;
+    e->world = world;
+    e->ipc = world > 1;
     return MCB_OK;
 }
 
-int mcb_european_peer_async(mcb_engine *e, const mcb_option_data *opt, uint64_t n_paths, uint64_t seed,
-                            int option_type, mcb_result *d_results, void *stream)
+int mcb_set_wait_timeout_ms(mcb_engine *e, uint64_t ms)
 {
-    int rc = check_common(e, opt);
-    if (rc) return rc;
-    if (e->peer_world < 1) return fail(MCB_ERR_INVALID, "peer mailboxes are not connected");
-    if (!d_results) return fail(MCB_ERR_INVALID, "d_results is NULL");
-    if (option_type != MCB_CALL && option_type != MCB_PUT) return fail(MCB_ERR_INVALID, "bad option_type");
-    n_paths = resolve_paths(opt, n_paths);
-    if (n_paths == 0) return fail(MCB_ERR_INVALID, "n_paths must be > 0");
-    DeviceGuard g(e->device);
-    cudaStream_t st = pick(e, stream);
-    const int rank = e->peer_rank, world = e->peer_world;
-    const uint64_t n_chunks = (n_paths + kEuropeanChunk - 1) / kEuropeanChunk;
-    int seg_lo, seg_hi;
-    uint64_t c_lo, c_hi;
-    segment_span(rank, world, n_chunks, &seg_lo, &seg_hi, &c_lo, &c_hi);
-    if ((rc = e->partials.reserve((size_t)(c_hi - c_lo) + 1))) return rc;
-    const EuropeanParams prm = european_params(opt, opt->K, opt->v, n_paths, seed, c_lo);
-    if ((rc = launch_european<MCB_EUROPEAN_PATHS_PER_SLOT>(e, prm, option_type, c_hi - c_lo, e->partials.ptr, nullptr,
-                                                           0, st)))
-        return rc;
-    const unsigned long long epoch = ++e->peer_epoch;
-    segment_peer_kernel<<<(unsigned)(seg_hi - seg_lo), kSlots, 0, st>>>(e->partials.ptr, c_lo, n_chunks, seg_lo, seg_hi,
-                                                                        e->peers, rank, world, epoch);
-    e->launches++;
-    CU(cudaGetLastError());
-    const double discount = std::exp(-(double)opt->r * (double)opt->T);
-    combine_peer_kernel<<<1, 32, 0, st>>>(e->mailbox, world, epoch, n_paths, discount,
-                                          reinterpret_cast<ResultDev *>(d_results));
-    e->launches++;
-    CU(cudaGetLastError());
+    if (!e || ms == 0) return fail(MCB_ERR_INVALID, "bad argument");
+    const size_t n = e->shards.empty() ? 1 : e->shards.size();
+    for (size_t i = 0; i < n; ++i) (e->shards.empty() ? e : e->shards[i])->timeout_ns = ms * 1000000ull;
     return MCB_OK;
 }
 
-int mcb_european_fused_peer_async(mcb_engine *e, const mcb_option_data *opt, uint64_t n_paths, uint64_t seed,
-                                  int option_type, mcb_result *d_results, void *stream)
+int mcb_peer_timeouts(mcb_engine *e, uint64_t *count)
 {
-    int rc = check_common(e, opt);
-    if (rc) return rc;
-    if (e->peer_world < 1) return fail(MCB_ERR_INVALID, "peer mailboxes are not connected");
-    if (!d_results) return fail(MCB_ERR_INVALID, "d_results is NULL");
-    if (option_type != MCB_CALL && option_type != MCB_PUT) return fail(MCB_ERR_INVALID, "bad option_type");
-    n_paths = resolve_paths(opt, n_paths);
+    if (!e || !count) return fail(MCB_ERR_INVALID, "NULL argument");
+    uint64_t total = 0;
+    const size_t n = e->shards.empty() ? 1 : e->shards.size();
+    for (size_t i = 0; i < n; ++i) {
+        mcb_engine *s = e->shards.empty() ? e : e->shards[i];
+        DeviceGuard g(s->device);
+        unsigned int t = 0;
+        CU(cudaMemcpy(&t, &s->mailbox->timeouts, sizeof(t), cudaMemcpyDeviceToHost));
+        total += t;
+    }
+    *count = total;
+    return MCB_OK;
+}
+
+// ---------------------------------------------------------------- the European job pipeline
+namespace {
+
+// One shard's launch of job `epoch`: european_job_kernel over the chunks it owns (or the publish-only
+// kernel when it owns none), on the shard's main stream.
+int submit_shard(mcb_engine *s, mcb_engine *L, const mcb_option_data *opt, uint64_t n_paths, uint64_t seed,
+                 int option_type, unsigned long long epoch)
+{
+    DeviceGuard g(s->device);
+    if (!g.ok) return fail(MCB_ERR_CUDA, "cudaSetDevice(%d) failed", s->device);
+    const int rank = s->rank, world = s->world;
+    const int slot = (int)(epoch % kRing);
     const uint64_t n_chunks = (n_paths + kEuropeanChunk - 1) / kEuropeanChunk;
-    // every segment needs at least one chunk for its "last CTA" to exist: small jobs take the 3-launch path
-    if (n_chunks < (uint64_t)MCB_SEGMENTS)
-        return mcb_european_peer_async(e, opt, n_paths, seed, option_type, d_results, stream);
-    DeviceGuard g(e->device);
-    cudaStream_t st = pick(e, stream);
-    const int rank = e->peer_rank, world = e->peer_world;
     int seg_lo, seg_hi;
     uint64_t c_lo, c_hi;
     segment_span(rank, world, n_chunks, &seg_lo, &seg_hi, &c_lo, &c_hi);
     if (c_hi - c_lo > 0x7fffffffull) return fail(MCB_ERR_INVALID, "too many chunks for one launch");
-    if ((rc = e->partials.reserve((size_t)(c_hi - c_lo) + 1))) return rc;
-    if (e->seg_tickets.cap == 0) {
-        if ((rc = e->seg_tickets.reserve(MCB_SEGMENTS))) return rc;
-        CU(cudaMemsetAsync(e->seg_tickets.ptr, 0, sizeof(unsigned int) * MCB_SEGMENTS, st));
-    }
-    const EuropeanParams prm = european_params(opt, opt->K, opt->v, n_paths, seed, c_lo);
-    FusedPeerArgs args{};
+    int rc;
+    if ((rc = s->partials.reserve((size_t)(c_hi - c_lo) + 1))) return rc;
+    // in-process groups pace themselves with events: the mailbox slot of job epoch - kRing must have
+    // been folded by the leader before this job's stores land in it (separate processes use acks)
+    if (s->in_process && epoch > (unsigned long long)kRing) CU(cudaStreamWaitEvent(s->stream, L->f_done[slot], 0));
+    JobArgs args{};
     args.n_chunks = n_chunks;
     args.n_paths = n_paths;
     args.discount = std::exp(-(double)opt->r * (double)opt->T);
-    args.seg_tickets = e->seg_tickets.ptr;
-    args.peers = e->peers;
-    args.out = reinterpret_cast<ResultDev *>(d_results);
-    args.epoch = ++e->peer_epoch;
-    args.seg_lo = seg_lo; args.seg_hi = seg_hi; args.rank = rank; args.world = world;
-    {
-        TimedScope timed(e, MCB_KERNEL_EUROPEAN, st);
-        if (option_type == MCB_PUT)
-            european_fused_peer_kernel<kPut, MCB_EUROPEAN_PATHS_PER_SLOT><<<(unsigned)(c_hi - c_lo), kSlots, 0, st>>>(
-                prm, args, e->partials.ptr);
-        else
-            european_fused_peer_kernel<kCall, MCB_EUROPEAN_PATHS_PER_SLOT><<<(unsigned)(c_hi - c_lo), kSlots, 0, st>>>(
-                prm, args, e->partials.ptr);
+    args.seg_tickets = s->seg_tickets;
+    args.peers = s->peers;
+    args.epoch = epoch;
+    args.timeout_ns = s->timeout_ns;
+    args.seg_lo = seg_lo;
+    args.seg_hi = seg_hi;
+    args.live_segments = 0;
+    for (int sg = seg_lo; sg < seg_hi; ++sg)
+        if ((n_chunks * (uint64_t)sg) / MCB_SEGMENTS != (n_chunks * (uint64_t)(sg + 1)) / MCB_SEGMENTS)
+            ++args.live_segments;
+    args.rank = rank;
+    args.world = world;
+    args.n_consumers = s->ipc ? world : 1;
+    args.check_acks = s->ipc ? 1 : 0;
+    if (world == 1) {
+        args.d_out = s->results.ptr;
+        args.h_out = &s->h_ring[epoch % kHostRing];
+        args.h_segments = s->h_segments;
     }
-    e->launches++;
+    if (c_hi > c_lo) {
+        const EuropeanParams prm = european_params(opt, opt->K, opt->v, n_paths, seed, c_lo);
+        TimedScope timed(s, MCB_KERNEL_EUROPEAN, s->stream);
+        if (option_type == MCB_PUT)
+            european_job_kernel<kPut, MCB_EUROPEAN_PATHS_PER_SLOT><<<(unsigned)(c_hi - c_lo), kSlots, 0, s->stream>>>(
+                prm, args, s->partials.ptr);
+        else
+            european_job_kernel<kCall, MCB_EUROPEAN_PATHS_PER_SLOT><<<(unsigned)(c_hi - c_lo), kSlots, 0, s->stream>>>(
+                prm, args, s->partials.ptr);
+    } else {
+        job_publish_empty_kernel<<<1, kSegments, 0, s->stream>>>(args);
+    }
+    L->launches++;
     CU(cudaGetLastError());
+    if (world > 1) CU(cudaEventRecord(s->p_done[slot], s->stream));
     return MCB_OK;
 }
 
-uint64_t mcb_launch_count(mcb_engine *e) { return e ? e->launches : 0; }
+size_t shard_count(const mcb_engine *e) { return e->shards.empty() ? 1 : e->shards.size(); }
+mcb_engine *shard_at(mcb_engine *e, size_t i) { return e->shards.empty() ? e : e->shards[i]; }
+
+}  // namespace
+
+int mcb_european_submit(mcb_engine *e, const mcb_option_data *opt, uint64_t n_paths, uint64_t seed, int option_type,
+                        uint64_t *ticket)
+{
+    int rc = check_common(e, opt);
+    if (rc) return rc;
+    if (e->leader) return fail(MCB_ERR_INVALID, "submit to the multi-device engine, not to one of its shards");
+    if (!ticket) return fail(MCB_ERR_INVALID, "ticket is NULL");
+    if (option_type != MCB_CALL && option_type != MCB_PUT) return fail(MCB_ERR_INVALID, "bad option_type");
+    n_paths = resolve_paths(opt, n_paths);
+    if (n_paths == 0) return fail(MCB_ERR_INVALID, "n_paths must be > 0");
+    // the epoch advances before anything that can fail, so that every rank of a group stays in step
+    const unsigned long long epoch = ++e->job_epoch;
+    *ticket = epoch;
+    HostSlot *hs = &e->h_ring[epoch % kHostRing];
+    hs->seq = 0;                      // the job that used this slot kHostRing tickets ago expires here
+    e->h_ring_paths[epoch % kHostRing] = n_paths;
+    std::atomic_thread_fence(std::memory_order_seq_cst);
+    const size_t n = shard_count(e);
+    for (size_t i = 0; i < n; ++i)
+        if ((rc = submit_shard(shard_at(e, i), e, opt, n_paths, seed, option_type, epoch))) return rc;
+    if (e->world > 1) {
+        DeviceGuard g(e->device);
+        const int slot = (int)(epoch % kRing);
+        for (size_t i = 0; i < n; ++i) CU(cudaStreamWaitEvent(e->f_stream, shard_at(e, i)->p_done[slot], 0));
+        combine_job_kernel<<<1, 32, 0, e->f_stream>>>(e->peers, e->rank, e->world, e->ipc ? 1 : 0, epoch, e->timeout_ns,
+                                                      n_paths, std::exp(-(double)opt->r * (double)opt->T),
+                                                      e->results.ptr, hs, e->h_segments);
+        e->launches++;
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(e->f_done[slot], e->f_stream));
+    }
+    return MCB_OK;
+}
+
+int mcb_european_collect(mcb_engine *e, uint64_t ticket, mcb_result *out)
+{
+    if (!e || !out) return fail(MCB_ERR_INVALID, "NULL argument");
+    if (ticket == 0 || ticket > e->job_epoch) return fail(MCB_ERR_INVALID, "unknown ticket %llu", (unsigned long long)ticket);
+    if (e->job_epoch - ticket >= (unsigned long long)kHostRing)
+        return fail(MCB_ERR_INVALID, "ticket %llu has expired (only the last %d results are kept)",
+                    (unsigned long long)ticket, kHostRing);
+    volatile HostSlot *hs = &e->h_ring[ticket % kHostRing];
+    // The result arrives in mapped host memory straight from the kernel: spin on its sequence word
+    // (no cudaStreamSynchronize round trip); every so often make sure the streams are still healthy.
+    const auto t0 = std::chrono::steady_clock::now();
+    unsigned long long spins = 0;
+    while (hs->seq != ticket) {
+        if ((++spins & 0x3fff) == 0) {
+            DeviceGuard g(e->device);
+            cudaError_t qa = cudaStreamQuery(e->stream), qb = cudaStreamQuery(e->f_stream);
+            if ((qa != cudaSuccess && qa != cudaErrorNotReady) || (qb != cudaSuccess && qb != cudaErrorNotReady))
+                return fail(MCB_ERR_CUDA, "stream failed while waiting for ticket %llu: %s", (unsigned long long)ticket,
+                            cudaGetErrorString(qa != cudaSuccess && qa != cudaErrorNotReady ? qa : qb));
+            if (qa == cudaSuccess && qb == cudaSuccess) {
+                bool idle = true;       // multi-device: every shard's stream must have drained too
+                for (size_t i = 1; i < shard_count(e) && idle; ++i) {
+                    DeviceGuard gs(shard_at(e, i)->device);
+                    idle = cudaStreamQuery(shard_at(e, i)->stream) == cudaSuccess;
+                }
+                if (idle && hs->seq != ticket) {
+                    std::atomic_thread_fence(std::memory_order_seq_cst);
+                    if (hs->seq != ticket)
+                        return fail(MCB_ERR_CUDA, "the streams are idle but ticket %llu never completed",
+                                    (unsigned long long)ticket);
+                }
+            }
+            const double waited = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            if (waited > 600.0) return fail(MCB_ERR_TIMEOUT, "ticket %llu: no result after 600 s", (unsigned long long)ticket);
+        }
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    memcpy(out, const_cast<const ResultDev *>(&hs->result), sizeof(mcb_result));
+    if (out->n_paths == 0 || out->price != out->price)
+        return fail(MCB_ERR_TIMEOUT, "ticket %llu: a peer did not deliver its segments within %.1f s (result poisoned)",
+                    (unsigned long long)ticket, (double)e->timeout_ns * 1e-9);
+    return MCB_OK;
+}
+
+int mcb_pipeline_timer_start(mcb_engine *e)
+{
+    if (!e) return fail(MCB_ERR_INVALID, "engine is NULL");
+    int rc = sync_all(e);
+    if (rc) return rc;
+    DeviceGuard g(e->device);
+    CU(cudaEventRecord(e->t_begin, e->stream));
+    // nothing of the timed jobs may start before t_begin, on any stream of any shard
+    CU(cudaStreamWaitEvent(e->f_stream, e->t_begin, 0));
+    for (size_t i = 1; i < shard_count(e); ++i) {
+        DeviceGuard gs(shard_at(e, i)->device);
+        CU(cudaStreamWaitEvent(shard_at(e, i)->stream, e->t_begin, 0));
+    }
+    return MCB_OK;
+}
+
+int mcb_pipeline_timer_stop(mcb_engine *e, double *elapsed_ms)
+{
+    if (!e || !elapsed_ms) return fail(MCB_ERR_INVALID, "NULL argument");
+    {
+        // the end of the timed region is when EVERY stream of every shard has drained
+        DeviceGuard g(e->device);
+        for (size_t i = 0; i < shard_count(e); ++i) {
+            mcb_engine *s = shard_at(e, i);
+            DeviceGuard gs(s->device);
+            cudaEvent_t tmp = nullptr;
+            CU(cudaEventCreateWithFlags(&tmp, cudaEventDisableTiming));
+            CU(cudaEventRecord(tmp, s->stream));
+            CU(cudaStreamWaitEvent(e->f_stream, tmp, 0));
+            CU(cudaEventDestroy(tmp));   // released once the wait has consumed it
+        }
+        CU(cudaEventRecord(e->t_end, e->f_stream));
+        CU(cudaEventSynchronize(e->t_end));
+        float ms = 0.0f;
+        CU(cudaEventElapsedTime(&ms, e->t_begin, e->t_end));
+        *elapsed_ms = (double)ms;
+    }
+    return MCB_OK;
+}
+
+uint64_t mcb_launch_count(mcb_engine *e)
+{
+    if (!e) return 0;
+    uint64_t total = 0;
+    for (size_t i = 0; i < shard_count(e); ++i) total += shard_at(e, i)->launches;
+    return total;
+}
 
 int mcb_timing_enable(mcb_engine *e, int on)
 {
@@ -691,15 +969,61 @@ static int finish_whole_job(mcb_engine *e, int n_sets, uint64_t n_paths, float r
 int mcb_price_european(mcb_engine *e, const mcb_option_data *opt, uint64_t n_paths, uint64_t seed, int option_type,
                        mcb_result *out)
 {
+    // ONE launch per shard; the result comes back through mapped host memory (no copy, no stream sync)
     if (!out) return fail(MCB_ERR_INVALID, "out is NULL");
-    int rc = check_common(e, opt);
+    uint64_t ticket = 0;
+    int rc = mcb_european_submit(e, opt, n_paths, seed, option_type, &ticket);
     if (rc) return rc;
-    DeviceGuard g(e->device);
-    n_paths = resolve_paths(opt, n_paths);
-    if ((rc = mcb_european_segments_async(e, opt, n_paths, seed, option_type, 0, 1, e->segments.ptr, nullptr)))
-        return rc;
-    return finish_whole_job(e, 1, n_paths, opt->r, opt->T, out);
+    return mcb_european_collect(e, ticket, out);
 }
+
+// Whole-job calls on a multi-device engine: every shard fills the segments it owns straight into the
+// LEADER's segment buffer (peer stores over NVLink from inside segment_kernel), the leader's stream
+// waits for the shards' events and runs the fixed final tree.  No collective library, same bits.
+// (The whole-job calls are synchronous, so the leader's buffer is free when the next one starts.)
+extern "C++" {
+template <typename F>
+static int run_on_shards(mcb_engine *e, F &&enqueue)
+{
+    const size_t n = shard_count(e);
+    int rc;
+    for (size_t i = 0; i < n; ++i) {
+        mcb_engine *s = shard_at(e, i);
+        DeviceGuard g(s->device);
+        if ((rc = enqueue(s, (int)i, (int)n))) return rc;
+        if (i) {
+            CU(cudaEventRecord(s->p_done[0], s->stream));
+            CU(cudaStreamWaitEvent(e->stream, s->p_done[0], 0));
+        }
+    }
+    return MCB_OK;
+}
+}  // extern "C++"
+
+// Slab-sharded modes (trajectories, nested MC) on a multi-device engine: one host thread per shard
+// drives that shard's own synchronous call on its slab of paths; rows are pure functions of
+// (seed, path id), so the slabs concatenate to the single-device result.  No collective.
+extern "C++" {
+template <typename F>
+static int threads_over_shards(mcb_engine *e, F &&body)
+{
+    const size_t n = shard_count(e);
+    std::vector<mcb_engine *> list;
+    for (size_t i = 0; i < n; ++i) list.push_back(shard_at(e, i));
+    std::vector<int> rcs(n, MCB_OK);
+    std::vector<std::string> msgs(n);
+    std::vector<std::thread> threads;
+    for (size_t i = 0; i < n; ++i)
+        threads.emplace_back([&, i]() {
+            rcs[i] = body(list[i], (int)i, (int)n);
+            if (rcs[i] != MCB_OK) msgs[i] = g_error;   // g_error is thread-local: carry the message over
+        });
+    for (auto &t : threads) t.join();
+    for (size_t i = 0; i < n; ++i)
+        if (rcs[i] != MCB_OK) return fail(rcs[i], "shard %zu (device %d): %s", i, list[i]->device, msgs[i].c_str());
+    return MCB_OK;
+}
+}  // extern "C++"
 
 // ---------------------------------------------------------------------------------- bullet
 static int bullet_params(const mcb_option_data *opt, uint64_t n_paths_end, uint64_t seed, int Ik, float Sk, int Tk,
@@ -723,8 +1047,9 @@ static int bullet_params(const mcb_option_data *opt, uint64_t n_paths_end, uint6
     return MCB_OK;
 }
 
-int mcb_bullet_segments_async(mcb_engine *e, const mcb_option_data *opt, uint64_t n_paths, uint64_t seed, int Ik,
-                              float Sk, int Tk, int rank, int world, double *d_segments, void *stream)
+static int bullet_segments_impl(mcb_engine *e, const mcb_option_data *opt, uint64_t n_paths, uint64_t seed, int Ik,
+                                float Sk, int Tk, int rank, int world, double *d_segments, void *stream,
+                                int write_unowned)
 {
     int rc = check_common(e, opt);
     if (rc) return rc;
@@ -751,7 +1076,13 @@ int mcb_bullet_segments_async(mcb_engine *e, const mcb_option_data *opt, uint64_
         e->launches++;
         CU(cudaGetLastError());
     }
-    return launch_segments(e, e->partials.ptr, 0, c_lo, n_chunks, seg_lo, seg_hi, 1, d_segments, st);
+    return launch_segments(e, e->partials.ptr, 0, c_lo, n_chunks, seg_lo, seg_hi, 1, d_segments, st, write_unowned);
+}
+
+int mcb_bullet_segments_async(mcb_engine *e, const mcb_option_data *opt, uint64_t n_paths, uint64_t seed, int Ik,
+                              float Sk, int Tk, int rank, int world, double *d_segments, void *stream)
+{
+    return bullet_segments_impl(e, opt, n_paths, seed, Ik, Sk, Tk, rank, world, d_segments, stream, 1);
 }
 
 int mcb_price_bullet(mcb_engine *e, const mcb_option_data *opt, uint64_t n_paths, uint64_t seed, int Ik, float Sk,
@@ -762,14 +1093,18 @@ int mcb_price_bullet(mcb_engine *e, const mcb_option_data *opt, uint64_t n_paths
     if (rc) return rc;
     DeviceGuard g(e->device);
     n_paths = resolve_paths(opt, n_paths);
-    if ((rc = mcb_bullet_segments_async(e, opt, n_paths, seed, Ik, Sk, Tk, 0, 1, e->segments.ptr, nullptr))) return rc;
+    double *dst = e->segments.ptr;
+    if ((rc = run_on_shards(e, [&](mcb_engine *s, int rank, int world) {
+             return bullet_segments_impl(s, opt, n_paths, seed, Ik, Sk, Tk, rank, world, dst, nullptr, world == 1);
+         })))
+        return rc;
     return finish_whole_job(e, 1, n_paths, opt->r, opt->T, out);
 }
 
 // ------------------------------------------------------------------------------------ sweep
-int mcb_sweep_segments_async(mcb_engine *e, const mcb_option_data *opt, const float *strikes, const float *vols,
-                             int n_params, uint64_t n_paths, uint64_t seed, int option_type, int rank, int world,
-                             double *d_segments, void *stream)
+static int sweep_segments_impl(mcb_engine *e, const mcb_option_data *opt, const float *strikes, const float *vols,
+                               int n_params, uint64_t n_paths, uint64_t seed, int option_type, int rank, int world,
+                               double *d_segments, void *stream, int write_unowned)
 {
     int rc = check_common(e, opt);
     if (rc) return rc;
@@ -839,10 +1174,18 @@ int mcb_sweep_segments_async(mcb_engine *e, const mcb_option_data *opt, const fl
             CU(cudaGetLastError());
         }
         if ((rc = launch_segments(e, e->partials.ptr, stride, c_lo, n_chunks, seg_lo, seg_hi, (int)cnt,
-                                  d_segments + i0 * 2 * MCB_SEGMENTS, st)))
+                                  d_segments + i0 * 2 * MCB_SEGMENTS, st, write_unowned)))
             return rc;
     }
     return MCB_OK;
+}
+
+int mcb_sweep_segments_async(mcb_engine *e, const mcb_option_data *opt, const float *strikes, const float *vols,
+                             int n_params, uint64_t n_paths, uint64_t seed, int option_type, int rank, int world,
+                             double *d_segments, void *stream)
+{
+    return sweep_segments_impl(e, opt, strikes, vols, n_params, n_paths, seed, option_type, rank, world, d_segments,
+                               stream, 1);
 }
 
 int mcb_price_sweep(mcb_engine *e, const mcb_option_data *opt, const float *strikes, const float *vols, int n_params,
@@ -855,8 +1198,11 @@ int mcb_price_sweep(mcb_engine *e, const mcb_option_data *opt, const float *stri
     DeviceGuard g(e->device);
     n_paths = resolve_paths(opt, n_paths);
     if ((rc = e->segments.reserve((size_t)n_params * 2 * MCB_SEGMENTS))) return rc;
-    if ((rc = mcb_sweep_segments_async(e, opt, strikes, vols, n_params, n_paths, seed, option_type, 0, 1,
-                                       e->segments.ptr, nullptr)))
+    double *dst = e->segments.ptr;
+    if ((rc = run_on_shards(e, [&](mcb_engine *s, int rank, int world) {
+             return sweep_segments_impl(s, opt, strikes, vols, n_params, n_paths, seed, option_type, rank, world, dst,
+                                        nullptr, world == 1);
+         })))
         return rc;
     return finish_whole_job(e, n_params, n_paths, opt->r, opt->T, out);
 }
@@ -906,6 +1252,9 @@ int mcb_trajectories_async(mcb_engine *e, const mcb_option_data *opt, uint64_t f
     return trajectories_launch(e, opt, first_path, n_paths, seed, d_prices, d_counts, nullptr, stream);
 }
 
+static int trajectories_to_host(mcb_engine *e, const mcb_option_data *opt, uint64_t first_path, uint64_t n_paths,
+                                uint64_t seed, float *prices, int *counts);
+
 int mcb_simulate_trajectories(mcb_engine *e, const mcb_option_data *opt, uint64_t first_path, uint64_t n_paths,
                               uint64_t seed, float *prices, int *counts, int where)
 {
@@ -921,6 +1270,23 @@ int mcb_simulate_trajectories(mcb_engine *e, const mcb_option_data *opt, uint64_
     }
     if (where != MCB_HOST) return fail(MCB_ERR_INVALID, "bad `where`");
     if (n_paths == 0) return MCB_OK;
+    if (shard_count(e) > 1) {   // multi-device engine: contiguous slabs, every shard copies its own rows home
+        const size_t row = (size_t)opt->N_STEPS;
+        return threads_over_shards(e, [&](mcb_engine *s, int rank, int world) {
+            const uint64_t lo = n_paths * (uint64_t)rank / (uint64_t)world, hi = n_paths * (uint64_t)(rank + 1) / (uint64_t)world;
+            if (hi == lo) return (int)MCB_OK;
+            return trajectories_to_host(s, opt, first_path + lo, hi - lo, seed, prices + lo * row,
+                                        counts ? counts + lo * row : nullptr);
+        });
+    }
+    return trajectories_to_host(e, opt, first_path, n_paths, seed, prices, counts);
+}
+
+static int trajectories_to_host(mcb_engine *e, const mcb_option_data *opt, uint64_t first_path, uint64_t n_paths,
+                                uint64_t seed, float *prices, int *counts)
+{
+    int rc;
+    DeviceGuard g(e->device);
     // Host destination: rows are pure functions of (seed, path id), so the job is cut into slabs of
     // <= 128 MB that go through the engine's grow-only workspace (no per-call cudaMalloc / cudaFree,
     // bounded device memory whatever n_paths is) and are copied back slab by slab.
@@ -994,6 +1360,10 @@ int mcb_nested_async(mcb_engine *e, const mcb_option_data *opt, uint64_t first_o
     return MCB_OK;
 }
 
+static int nested_single(mcb_engine *e, const mcb_option_data *opt, uint64_t first_outer, uint64_t n_outer,
+                         uint64_t seed_outer, uint64_t seed_inner, int discount_mode, float *F, float *prices,
+                         int *counts, int where, double *mean_F);
+
 int mcb_nested_monte_carlo(mcb_engine *e, const mcb_option_data *opt, uint64_t first_outer, uint64_t n_outer,
                            uint64_t seed_outer, uint64_t seed_inner, int discount_mode, float *F, float *prices,
                            int *counts, int where, double *mean_F)
@@ -1009,6 +1379,35 @@ int mcb_nested_monte_carlo(mcb_engine *e, const mcb_option_data *opt, uint64_t f
         if (mean_F) *mean_F = 0.0;
         return MCB_OK;
     }
+    if (shard_count(e) > 1 && where == MCB_HOST) {
+        // multi-device engine: outer trajectory p and everything hanging off it depend on p only
+        const size_t row = (size_t)opt->N_STEPS;
+        rc = threads_over_shards(e, [&](mcb_engine *s, int rank, int world) {
+            const uint64_t lo = n_outer * (uint64_t)rank / (uint64_t)world, hi = n_outer * (uint64_t)(rank + 1) / (uint64_t)world;
+            if (hi == lo) return (int)MCB_OK;
+            return nested_single(s, opt, first_outer + lo, hi - lo, seed_outer, seed_inner, discount_mode,
+                                 F + lo * row, prices ? prices + lo * row : nullptr,
+                                 counts ? counts + lo * row : nullptr, MCB_HOST, nullptr);
+        });
+        if (rc) return rc;
+        if (mean_F) {
+            double acc = 0.0;
+            for (size_t i = 0; i < n; ++i) acc += (double)F[i];
+            *mean_F = acc / (double)(n + 1);
+        }
+        return MCB_OK;
+    }
+    return nested_single(e, opt, first_outer, n_outer, seed_outer, seed_inner, discount_mode, F, prices, counts, where,
+                         mean_F);
+}
+
+static int nested_single(mcb_engine *e, const mcb_option_data *opt, uint64_t first_outer, uint64_t n_outer,
+                         uint64_t seed_outer, uint64_t seed_inner, int discount_mode, float *F, float *prices,
+                         int *counts, int where, double *mean_F)
+{
+    int rc;
+    DeviceGuard g(e->device);
+    const size_t n = (size_t)n_outer * (size_t)opt->N_STEPS;
     float *dF = F, *dP = prices;
     int *dC = counts;
     std::vector<float> hostF;

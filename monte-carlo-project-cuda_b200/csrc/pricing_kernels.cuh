@@ -341,7 +341,8 @@ bullet_kernel(const __grid_constant__ WalkParams prm, float2 *__restrict__ parti
 // Final passes (replace the float atomicAdd / host loop of the reference).
 // segment_kernel: CTA s folds the chunk partials of segment s in double, fixed order.
 //   partials is indexed by (chunk - partials_first_chunk); segments outside [seg_lo, seg_hi)
-//   are written as +0.0 so a sum-allreduce over ranks reproduces every segment exactly.
+//   are written as +0.0 so a sum-allreduce over ranks reproduces every segment exactly
+//   (or left alone, write_unowned == 0, when the shards share one destination buffer).
 // combine_kernel: one warp folds the 64 segments and finalises price + standard error.
 // Both are batched over parameter sets with blockIdx.y / blockIdx.x.
 // ------------------------------------------------------------------------------------------
@@ -349,12 +350,15 @@ constexpr int kSegments = 64;  // MCB_SEGMENTS
 
 __global__ void __launch_bounds__(kSlots)
 segment_kernel(const float2 *__restrict__ partials, uint64_t partials_stride, uint64_t partials_first_chunk,
-               uint64_t n_chunks, int seg_lo, int seg_hi, double *__restrict__ segments)
+               uint64_t n_chunks, int seg_lo, int seg_hi, int write_unowned, double *__restrict__ segments)
 {
     __shared__ double scratch[2 * kWarps];
     const int seg = blockIdx.x;
     const int set = blockIdx.y;
     double a = 0.0, b = 0.0;
+    // write_unowned == 0: `segments` is shared by several shards (the leader's buffer, written over
+    // NVLink by the others); every shard writes exactly the segments it owns
+    if (!write_unowned && (seg < seg_lo || seg >= seg_hi)) return;   // CTA-uniform
     if (seg >= seg_lo && seg < seg_hi) {
         const uint64_t lo = (n_chunks * (uint64_t)seg) / kSegments;
         const uint64_t hi = (n_chunks * (uint64_t)(seg + 1)) / kSegments;
@@ -370,54 +374,6 @@ segment_kernel(const float2 *__restrict__ partials, uint64_t partials_stride, ui
         double *dst = segments + ((uint64_t)set * kSegments + seg) * 2;
         dst[0] = a;
         dst[1] = b;
-    }
-}
-
-// ---- peer-memory exchange (see include/mcb200.h, "NCCL-free exchange") ------------------------
-constexpr int kMaxPeers = 16;  // MCB_MAX_PEERS
-struct PeerMailbox {           // one per rank, in that rank's HBM, written by every peer over NVLink
-    double gather[2][kSegments * 2];            // parity-buffered (sum, sumsq) segments
-    unsigned long long flags[2][kMaxPeers];     // flags[parity][r] = last epoch rank r has published
-    unsigned int ticket;                        // local: CTAs of the segment pass that have finished
-};
-struct PeerTable {
-    PeerMailbox *box[kMaxPeers];                // box[r] = rank r's mailbox as mapped into this process
-};
-
-// Segment pass that all-gathers by peer stores: CTA s folds segment s exactly like segment_kernel
-// when this rank owns it and writes the pair into EVERY rank's mailbox; the last owning CTA to
-// finish publishes this rank's epoch flag everywhere.
-__global__ void __launch_bounds__(kSlots)
-segment_peer_kernel(const float2 *__restrict__ partials, uint64_t partials_first_chunk, uint64_t n_chunks, int seg_lo,
-                    int seg_hi, PeerTable peers, int rank, int world, unsigned long long epoch)
-{
-    __shared__ double scratch[2 * kWarps];
-    const int seg = seg_lo + blockIdx.x;       // grid = owned segments only
-    const int parity = (int)(epoch & 1ull);
-    double a = 0.0, b = 0.0;
-    const uint64_t lo = (n_chunks * (uint64_t)seg) / kSegments;
-    const uint64_t hi = (n_chunks * (uint64_t)(seg + 1)) / kSegments;
-    for (uint64_t c = lo + threadIdx.x; c < hi; c += kSlots) {
-        const float2 v = partials[c - partials_first_chunk];
-        a = a + (double)v.x;
-        b = b + (double)v.y;
-    }
-    block_fold2(a, b, scratch);
-    if (threadIdx.x == 0) {
-        for (int r = 0; r < world; ++r) {
-            double *dst = peers.box[r]->gather[parity] + 2 * seg;
-            __stcg(dst, a);
-            __stcg(dst + 1, b);
-        }
-        __threadfence_system();                 // my segment is visible everywhere before I take a ticket
-        PeerMailbox *mine = peers.box[rank];
-        const unsigned int owned = (unsigned int)(seg_hi - seg_lo);
-        if (atomicAdd(&mine->ticket, 1u) == owned - 1u) {
-            mine->ticket = 0u;                  // ready for the next call (stream-ordered)
-            __threadfence_system();
-            for (int r = 0; r < world; ++r)
-                *((volatile unsigned long long *)&peers.box[r]->flags[parity][rank]) = epoch;
-        }
     }
 }
 
@@ -451,29 +407,91 @@ combine_kernel(const double *__restrict__ segments, uint64_t n_paths, double dis
     }
 }
 
-// Final pass behind segment_peer_kernel: wait (bounded) until every rank has published `epoch` in
-// MY mailbox, then the same fixed tree as combine_kernel.  On timeout n_paths is reported as 0.
-__global__ void __launch_bounds__(32)
-combine_peer_kernel(PeerMailbox *__restrict__ mine, int world, unsigned long long epoch, uint64_t n_paths,
-                    double discount, ResultDev *__restrict__ out)
+// ------------------------------------------------------------------------------------------
+// The European JOB pipeline (mcb_european_submit / mcb_european_collect; one launch per shard).
+//
+// A job is priced by `world` shards (GPUs), shard g owning the chunks of segments
+// [64g/world, 64(g+1)/world).  european_job_kernel is european_kernel's chunk loop plus, through
+// tickets and with no second launch:
+//   * the last CTA of every segment folds that segment (same order as segment_kernel) and STORES
+//     the (sum, sumsq) pair into the mailbox slot of every consumer shard -- its own HBM, or a
+//     peer's over NVLink / NVSwitch (plain st.global on a peer-mapped address);
+//   * the CTA that completes the shard's last segment writes +0.0 into owned segments that have
+//     no chunk, fences and publishes the job's epoch flag in every consumer's mailbox;
+//   * with world == 1 that same CTA runs the final tree (same order as combine_kernel) and
+//     writes the result to device memory and to a mapped host slot: ONE launch per price.
+// With world > 1 the final tree is combine_job_kernel on the consumer's OWN second stream: it
+// waits (bounded by a %globaltimer deadline) for the `world` flags, folds, writes the result and
+// acknowledges the slot to every producer.  The pricing stream never waits for a peer, so rank
+// skew and NVLink latency hide behind the next job's pricing; a ring of kRing mailbox slots
+// lets a shard run kRing - 1 jobs ahead of the slowest consumer.
+// The cold tail lives in a __noinline__ function so that the hot loop keeps its 8 CTAs per SM.
+// ------------------------------------------------------------------------------------------
+constexpr int kMaxPeers = 16;  // MCB_MAX_PEERS
+constexpr int kRing = 4;       // MCB_PIPELINE_DEPTH: mailbox slots = jobs in flight per engine
+
+struct PeerMailbox {           // one per shard, in that shard's HBM; written by every producer shard
+    double gather[kRing][kSegments * 2];               // (sum, sumsq) segments of the job in each slot
+    unsigned long long flags[kRing][kMaxPeers];        // flags[slot][r] = last epoch producer r published there
+    unsigned long long consumed[kMaxPeers];            // consumed[c] = last epoch consumer c folded (its ack to ME)
+    unsigned int timeouts;                             // bounded waits that ran out (sticky, diagnostic)
+};
+struct PeerTable {
+    PeerMailbox *box[kMaxPeers];                       // box[r] = shard r's mailbox as mapped here
+};
+
+struct HostSlot {              // mapped pinned host memory, one per job in flight (64 bytes)
+    ResultDev result;
+    unsigned long long seq;    // == epoch once `result` is complete (written last, after a system fence)
+    unsigned long long pad[2];
+};
+
+struct JobArgs {
+    uint64_t n_chunks;              // chunks of the WHOLE job (segment boundaries are global)
+    uint64_t n_paths;
+    double discount;
+    unsigned int *seg_tickets;      // [kSegments] + [1] (shard ticket), all zero between launches
+    PeerTable peers;
+    ResultDev *d_out;               // world == 1: device copy of the result (nullable)
+    HostSlot *h_out;                // world == 1: mapped host slot (nullable)
+    double *h_segments;             // world == 1: mapped host [kSegments][2] (nullable)
+    unsigned long long epoch;       // job number, > 0, agreed by every shard
+    unsigned long long timeout_ns;  // bound of every device-side wait
+    int seg_lo, seg_hi;             // segments this shard owns
+    int live_segments;              // ... of which have at least one chunk
+    int rank, world;
+    int n_consumers;                // shards [0, n_consumers) receive the segments (world: all-gather; 1: gather)
+    int check_acks;                 // producers wait for the consumers' acks of job epoch - kRing (separate processes)
+};
+
+__device__ __forceinline__ unsigned long long global_timer_ns()
 {
-    const int lane = threadIdx.x;
-    const int parity = (int)(epoch & 1ull);
-    bool ok = true;
-    if (lane < world) {
-        const volatile unsigned long long *flag = &mine->flags[parity][lane];
-        unsigned int spins = 0;
-        while (*flag < epoch) {
-            if (++spins > (1u << 24)) {         // ~seconds: a peer never arrived
-                ok = false;
-                break;
-            }
-            __nanosleep(100);
-        }
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Spin (with back-off) until *p >= want or timeout_ns has passed.  The word lives in THIS GPU's
+// memory and is written by a peer over NVLink; volatile loads read it at L2.
+__device__ __noinline__ bool wait_at_least(const volatile unsigned long long *p, unsigned long long want,
+                                           unsigned long long timeout_ns)
+{
+    if (*p >= want) return true;
+    const unsigned long long t0 = global_timer_ns();
+    unsigned int ns = 32;
+    while (*p < want) {
+        if (global_timer_ns() - t0 > timeout_ns) return false;
+        __nanosleep(ns);
+        if (ns < 1024) ns <<= 1;
     }
-    ok = __all_sync(kFullMask, ok);
-    __threadfence_system();
-    const volatile double *seg = mine->gather[parity];
+    return true;
+}
+
+// The fixed 64 -> 1 tree of combine_kernel, run by one warp on a mailbox slot; ok == false (a
+// peer never arrived) poisons the result with NaN and n_paths = 0 instead of a plausible number.
+__device__ __forceinline__ void final_tree_warp(const volatile double *seg, int lane, uint64_t n_paths, double discount,
+                                                bool ok, unsigned long long epoch, ResultDev *d_out, HostSlot *h_out)
+{
     double s = seg[2 * lane] + seg[2 * (lane + 32)];
     double q = seg[2 * lane + 1] + seg[2 * (lane + 32) + 1];
     s = warp_fold(s);
@@ -485,36 +503,28 @@ combine_peer_kernel(PeerMailbox *__restrict__ mine, int world, unsigned long lon
         var = var > 0.0 ? var : 0.0;
         if (n_paths > 1) var *= n / (n - 1.0);
         ResultDev r;
-        r.price = discount * mean;
-        r.std_error = discount * sqrt(var / n);
-        r.sum = s;
-        r.sumsq = q;
+        const double nan = __longlong_as_double(0x7ff8000000000000ll);
+        r.price = ok ? discount * mean : nan;
+        r.std_error = ok ? discount * sqrt(var / n) : nan;
+        r.sum = ok ? s : nan;
+        r.sumsq = ok ? q : nan;
         r.n_paths = ok ? n_paths : 0;
-        out[0] = r;
+        if (d_out) *d_out = r;
+        if (h_out) {
+            volatile double *hd = reinterpret_cast<volatile double *>(&h_out->result);
+            hd[0] = r.price;
+            hd[1] = r.std_error;
+            hd[2] = r.sum;
+            hd[3] = r.sumsq;
+            *reinterpret_cast<volatile unsigned long long *>(&h_out->result.n_paths) = r.n_paths;
+            __threadfence_system();
+            *reinterpret_cast<volatile unsigned long long *>(&h_out->seq) = epoch;
+        }
     }
 }
 
-// ------------------------------------------------------------------------------------------
-// ONE kernel for pricing + exchange at N > 1 (mcb_european_fused_peer_async): european_kernel's
-// chunk loop, then -- through tickets, no second launch -- the last CTA of every segment folds
-// that segment (same order as segment_kernel), stores it into every peer's mailbox over NVLink,
-// and the CTA that completes this rank's last segment publishes the epoch flag, waits (bounded)
-// for the peers' flags in its own mailbox and runs the final tree (same order as combine_kernel).
-// The cold tail lives in a __noinline__ function so that the hot loop keeps its 8 CTAs per SM.
-// ------------------------------------------------------------------------------------------
-struct FusedPeerArgs {
-    uint64_t n_chunks;              // chunks of the WHOLE job (segment boundaries are global)
-    uint64_t n_paths;
-    double discount;
-    unsigned int *seg_tickets;      // [kSegments], zero between launches
-    PeerTable peers;
-    ResultDev *out;
-    unsigned long long epoch;
-    int seg_lo, seg_hi, rank, world;
-};
-
-__device__ __noinline__ void fused_peer_tail(const FusedPeerArgs &args, const float2 *__restrict__ partials,
-                                             uint64_t first_chunk, double *dscratch, int *flag)
+__device__ __noinline__ void job_tail(const JobArgs &args, const float2 *__restrict__ partials, uint64_t first_chunk,
+                                      double *dscratch, int *flag)
 {
     const uint64_t chunk = first_chunk + blockIdx.x;
     const uint64_t n = args.n_chunks;
@@ -539,69 +549,62 @@ __device__ __noinline__ void fused_peer_tail(const FusedPeerArgs &args, const fl
         b = b + (double)v.y;
     }
     block_fold2(a, b, dscratch);
-    const int parity = (int)(args.epoch & 1ull);
+    const int slot = (int)(args.epoch % (unsigned long long)kRing);
     PeerMailbox *mine = args.peers.box[args.rank];
     if (threadIdx.x == 0) {
         args.seg_tickets[seg] = 0u;                         // ready for the next launch
-        for (int r = 0; r < args.world; ++r) {
-            double *dst = args.peers.box[r]->gather[parity] + 2 * seg;
+        for (int c = 0; c < args.n_consumers; ++c) {
+            // the slot still holds job epoch - kRing until consumer c has folded it
+            if (args.check_acks && args.epoch > (unsigned long long)kRing &&
+                !wait_at_least(&mine->consumed[c], args.epoch - kRing, args.timeout_ns)) {
+                atomicAdd(&mine->timeouts, 1u);
+                continue;                                   // c will time out on this job and report NaN
+            }
+            double *dst = args.peers.box[c]->gather[slot] + 2 * seg;
             __stcg(dst, a);
             __stcg(dst + 1, b);
         }
-        __threadfence_system();
-        const unsigned int owned = (unsigned int)(args.seg_hi - args.seg_lo);
-        const bool last = atomicAdd(&mine->ticket, 1u) == owned - 1u;
-        if (last) {
-            mine->ticket = 0u;
-            __threadfence_system();
-            for (int r = 0; r < args.world; ++r)
-                *((volatile unsigned long long *)&args.peers.box[r]->flags[parity][args.rank]) = args.epoch;
-        }
-        flag[1] = last ? 1 : 0;
+        if (args.world > 1) __threadfence_system(); else __threadfence();
+        flag[1] = atomicAdd(&args.seg_tickets[kSegments], 1u) == (unsigned int)args.live_segments - 1u ? 1 : 0;
     }
     __syncthreads();
-    if (!flag[1] || threadIdx.x >= 32) return;
-    // the last CTA of this rank: wait for every rank's flag in MY mailbox, then the final tree
-    const int lane = threadIdx.x;
-    bool ok = true;
-    if (lane < args.world) {
-        const volatile unsigned long long *f = &mine->flags[parity][lane];
-        unsigned int spins = 0;
-        while (*f < args.epoch) {
-            if (++spins > (1u << 24)) {
-                ok = false;
-                break;
+    if (!flag[1]) return;
+    // ---- the CTA that completed this shard's last segment ------------------------------------
+    __threadfence();
+    if (args.live_segments < args.seg_hi - args.seg_lo) {   // owned segments without a chunk hold +0.0
+        for (int s = args.seg_lo + (int)threadIdx.x; s < args.seg_hi; s += kSlots) {
+            if ((n * (uint64_t)s) / kSegments == (n * (uint64_t)(s + 1)) / kSegments) {
+                for (int c = 0; c < args.n_consumers; ++c) {
+                    double *dst = args.peers.box[c]->gather[slot] + 2 * s;
+                    __stcg(dst, 0.0);
+                    __stcg(dst + 1, 0.0);
+                }
             }
-            __nanosleep(100);
         }
+        if (args.world > 1) __threadfence_system(); else __threadfence();
+        __syncthreads();
     }
-    ok = __all_sync(kFullMask, ok);
-    __threadfence_system();
-    const volatile double *sg = mine->gather[parity];
-    double s = sg[2 * lane] + sg[2 * (lane + 32)];
-    double q = sg[2 * lane + 1] + sg[2 * (lane + 32) + 1];
-    s = warp_fold(s);
-    q = warp_fold(q);
-    if (lane == 0) {
-        const double np = (double)args.n_paths;
-        const double mean = s / np;
-        double var = q / np - mean * mean;
-        var = var > 0.0 ? var : 0.0;
-        if (args.n_paths > 1) var *= np / (np - 1.0);
-        ResultDev r;
-        r.price = args.discount * mean;
-        r.std_error = args.discount * sqrt(var / np);
-        r.sum = s;
-        r.sumsq = q;
-        r.n_paths = ok ? args.n_paths : 0;
-        args.out[0] = r;
+    if (threadIdx.x == 0) args.seg_tickets[kSegments] = 0u;
+    if (args.world > 1) {
+        if (threadIdx.x < (unsigned)args.n_consumers)
+            *((volatile unsigned long long *)&args.peers.box[threadIdx.x]->flags[slot][args.rank]) = args.epoch;
+        return;
+    }
+    // world == 1: every segment is here; finish the job in this launch
+    const volatile double *sg = mine->gather[slot];
+    if (args.h_segments && threadIdx.x < 2 * kSegments)
+        reinterpret_cast<volatile double *>(args.h_segments)[threadIdx.x] = sg[threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        if (args.h_segments) __threadfence_system();
+        final_tree_warp(sg, (int)threadIdx.x, args.n_paths, args.discount, true, args.epoch, args.d_out, args.h_out);
     }
 }
 
 template <int TYPE, int PPS>
 __global__ void __launch_bounds__(kSlots, 8)
-european_fused_peer_kernel(const __grid_constant__ EuropeanParams prm, const __grid_constant__ FusedPeerArgs args,
-                           float2 *__restrict__ partials)
+european_job_kernel(const __grid_constant__ EuropeanParams prm, const __grid_constant__ JobArgs args,
+                    float2 *__restrict__ partials)
 {
     __shared__ float scratch[2 * kWarps];
     __shared__ double dscratch[2 * kWarps];
@@ -633,7 +636,71 @@ european_fused_peer_kernel(const __grid_constant__ EuropeanParams prm, const __g
     }
     block_fold2(sum, sq, scratch);
     if (threadIdx.x == 0) partials[blockIdx.x] = make_float2(sum, sq);
-    fused_peer_tail(args, partials, prm.first_chunk, dscratch, flag);
+    job_tail(args, partials, prm.first_chunk, dscratch, flag);
+}
+
+// A shard that owns no chunk of a (small) job still owes its consumers +0.0 segments and its flag.
+__global__ void __launch_bounds__(kSegments)
+job_publish_empty_kernel(const __grid_constant__ JobArgs args)
+{
+    const int slot = (int)(args.epoch % (unsigned long long)kRing);
+    PeerMailbox *mine = args.peers.box[args.rank];
+    __shared__ int ok;
+    if (threadIdx.x == 0) {
+        ok = 1;
+        for (int c = 0; c < args.n_consumers; ++c)
+            if (args.check_acks && args.epoch > (unsigned long long)kRing &&
+                !wait_at_least(&mine->consumed[c], args.epoch - kRing, args.timeout_ns)) {
+                atomicAdd(&mine->timeouts, 1u);
+                ok = 0;
+            }
+    }
+    __syncthreads();
+    if (!ok) return;
+    const int s = args.seg_lo + (int)threadIdx.x;
+    if (s < args.seg_hi) {
+        for (int c = 0; c < args.n_consumers; ++c) {
+            double *dst = args.peers.box[c]->gather[slot] + 2 * s;
+            __stcg(dst, 0.0);
+            __stcg(dst + 1, 0.0);
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < (unsigned)args.n_consumers)
+        *((volatile unsigned long long *)&args.peers.box[threadIdx.x]->flags[slot][args.rank]) = args.epoch;
+}
+
+// Final pass of a world > 1 job on consumer shard `rank`: wait (bounded) until every producer has
+// published `epoch` in MY mailbox, run the fixed tree, write the result (device + mapped host),
+// then acknowledge the slot to every producer.
+__global__ void __launch_bounds__(32)
+combine_job_kernel(PeerTable peers, int rank, int world, int spin, unsigned long long epoch,
+                   unsigned long long timeout_ns, uint64_t n_paths, double discount, ResultDev *__restrict__ d_out,
+                   HostSlot *__restrict__ h_out, double *__restrict__ h_segments)
+{
+    const int lane = threadIdx.x;
+    const int slot = (int)(epoch % (unsigned long long)kRing);
+    PeerMailbox *mine = peers.box[rank];
+    bool ok = true;
+    if (lane < world) {
+        const volatile unsigned long long *f = &mine->flags[slot][lane];
+        // spin == 0: the producers' launches were awaited through events (same process), the flag must be there
+        ok = spin ? wait_at_least(f, epoch, timeout_ns) : (*f >= epoch);
+        if (!ok) atomicAdd(&mine->timeouts, 1u);
+    }
+    ok = __all_sync(kFullMask, ok);
+    __threadfence_system();
+    const volatile double *sg = mine->gather[slot];
+    if (h_segments) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) reinterpret_cast<volatile double *>(h_segments)[lane + 32 * i] = sg[lane + 32 * i];
+        __threadfence_system();
+    }
+    final_tree_warp(sg, lane, n_paths, discount, ok, epoch, d_out, h_out);
+    __syncwarp();
+    // the slot may be overwritten by job epoch + kRing once every producer sees this ack
+    if (lane < world) *((volatile unsigned long long *)&peers.box[lane]->consumed[rank]) = epoch;
 }
 
 // Standalone deterministic float sum (reduce3..6 replacement): slot t adds x[t], x[t+256], ...

@@ -1,4 +1,4 @@
-"""Multi-GPU pricing: one process per GPU, paths sharded by index, ONE sum-allreduce.
+"""Multi-GPU pricing: one process per GPU, paths sharded by index, ONE exchange of 1 KiB.
 
 The reference is single-GPU ("Parallelism strategies: none"); this is the
 additive capability north_star asks for.  Every path is a pure function of (seed, path id), so
@@ -16,22 +16,34 @@ from __future__ import annotations
 
 import ctypes as C
 
-from . import (CALL, SEGMENTS, Engine, Result, path_span)  # noqa: F401  (re-exported helpers)
+from . import (CALL, SEGMENTS, Engine, McbError, Result, path_span)  # noqa: F401  (re-exported helpers)
 
 
 class ShardedPricer:
     """European / bullet / sweep pricing over the ranks of a ``torch.distributed`` group.
 
-    All work is enqueued on ``torch.cuda.current_stream()`` of this rank's device: kernel ->
-    all_reduce -> final tree, with no host synchronisation in between.  The C-ABI reads a NULL
-    stream as "the engine's own stream", so callers must make a real (non-default) torch stream
-    current -- ``with torch.cuda.stream(pricer.stream):`` -- before enqueueing.
+    ``transport`` says how the 64 (sum, sumsq) segments of a European job cross GPUs:
+
+    * ``"peer"`` -- the engine's job pipeline (``mcb_european_submit`` / ``collect``): every rank's
+      pricing kernel stores the segments it owns straight into every rank's mailbox over NVLink
+      (CUDA-IPC mapped peer memory) and the final tree runs on the engine's second stream; ONE pricing
+      launch per job, no collective library, the pricing stream never waits for a peer;
+    * ``"nccl"`` -- segment pass, one ``all_reduce(SUM)`` of the 1 KiB segment vector, final tree,
+      all enqueued on ``torch.cuda.current_stream()``;
+    * ``"auto"`` (default) -- ``"peer"`` when CUDA IPC connects on EVERY rank, else ``"nccl"``.
+
+    Both give the bits of a single-GPU run.  Bullet and sweep always take the all-reduce path.
+    For the all-reduce path the C-ABI reads a NULL stream as "the engine's own stream", so callers must
+    make a real (non-default) torch stream current -- ``with torch.cuda.stream(pricer.stream):``.
+    The peer path needs at most one rank per GPU and a world of at most 16.
     """
 
-    def __init__(self, engine: Engine, group=None, max_sets: int = 1, transport: str = "nccl"):
+    def __init__(self, engine: Engine, group=None, max_sets: int = 1, transport: str = "auto"):
         import torch
         import torch.distributed as dist
 
+        if transport not in ("auto", "nccl", "peer"):
+            raise ValueError("transport must be 'auto', 'nccl' or 'peer'")
         self.torch = torch
         self.dist = dist
         self.engine = engine
@@ -43,19 +55,47 @@ class ShardedPricer:
             self.rank, self.world = 0, 1
         self.device = torch.device("cuda", engine.device)
         self.stream = torch.cuda.Stream(self.device)
-        self._reserve(max_sets)
-        # transport "peer": the 64 segments are all-gathered by direct NVLink stores into CUDA-IPC
-        # mapped peer mailboxes inside the segment pass (European pricing only); "fused": the same from
-        # inside the pricing kernel itself (one launch per price); "nccl": all_reduce
-        self.transport = transport
-        if transport in ("peer", "fused") and self.world > 1:
-            handle = engine.peer_mailbox_create()
-            handles = [None] * self.world
-            dist.all_gather_object(handles, handle, group=group)
-            engine.peer_mailbox_connect(self.rank, self.world, handles)
-            dist.barrier(group=group)   # every mailbox is mapped everywhere before the first store
-        elif transport not in ("nccl", "peer", "fused"):
-            raise ValueError("transport must be 'nccl', 'peer' or 'fused'")
+        with torch.cuda.stream(self.stream):     # the buffers are zeroed on the stream that will use them
+            self._reserve(max_sets)
+        self.stream.synchronize()
+        self._ticket = None
+        self.transport = "nccl"
+        if self.world == 1:
+            self.transport = "peer"              # a group of one: the plain single-launch pipeline
+        elif transport in ("auto", "peer"):
+            self.transport = "peer" if self._connect_peers(strict=transport == "peer") else "nccl"
+
+    def _connect_peers(self, strict: bool) -> bool:
+        """CUDA-IPC mailbox exchange; every rank ends up in the same mode."""
+        dist, eng = self.dist, self.engine
+        mine = {"handle": None, "epoch": eng.peer_epoch(), "error": None}
+        try:
+            if self.world > 16:
+                raise McbError(1, "the peer transport supports at most 16 ranks")
+            mine["handle"] = eng.peer_mailbox_create()
+        except McbError as exc:
+            mine["error"] = str(exc)
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, mine, group=self.group)
+        ok = all(x["error"] is None for x in everyone)
+        base = max(x["epoch"] for x in everyone)
+        err = None
+        if ok:
+            try:
+                eng.peer_mailbox_connect(self.rank, self.world, [x["handle"] for x in everyone], base)
+            except McbError as exc:
+                err = str(exc)
+        results = [None] * self.world
+        dist.all_gather_object(results, err, group=self.group)   # also the barrier after connect
+        ok = ok and all(x is None for x in results)
+        if not ok:
+            # back to a group of one, so that engine.price_european keeps working on this rank
+            eng.peer_mailbox_connect(0, 1, [eng.peer_mailbox_create()], eng.peer_epoch())
+            if strict:
+                raise McbError(2, "peer transport unavailable: " + "; ".join(
+                    str(x) for x in ([y["error"] for y in everyone] + results) if x))
+        dist.barrier(group=self.group)
+        return ok
 
     def _reserve(self, n_sets: int):
         t = self.torch
@@ -77,15 +117,23 @@ class ShardedPricer:
         self.engine.combine_segments_async(self.segments.data_ptr(), n_sets, n_paths, r, T,
                                            self.results.data_ptr(), self._stream())
 
-    # ---- enqueue-only (device-resident result in self.results) ---------------------------
+    # ---- enqueue-only ---------------------------------------------------------------------
     def european_async(self, opt, n_paths, seed=1234, option_type=CALL):
-        if self.transport in ("peer", "fused") and self.world > 1:
-            self.engine.european_peer_async(opt, n_paths, seed, option_type, self.results.data_ptr(), self._stream(),
-                                            fused=self.transport == "fused")
+        """Enqueue one European job; ``european_result()`` fetches the latest one."""
+        if self.transport == "peer":
+            self._ticket = self.engine.european_submit(opt, n_paths, seed, option_type)
             return
+        self._ticket = None
         self.engine.european_segments_async(opt, n_paths, seed, option_type, self.rank, self.world,
                                             self.segments.data_ptr(), self._stream())
         self._finish_async(1, n_paths, opt.r, opt.T)
+
+    def european_result(self) -> Result:
+        if self.transport == "peer":
+            if self._ticket is None:
+                raise RuntimeError("no European job has been submitted")
+            return self.engine.european_collect(self._ticket)
+        return self._fetch(1)[0]
 
     def bullet_async(self, opt, n_paths, seed=1234, Ik=0, Sk=0.0, Tk=0):
         self.engine.bullet_segments_async(opt, n_paths, seed, Ik, Sk, Tk, self.rank, self.world,
@@ -95,7 +143,9 @@ class ShardedPricer:
     def sweep_async(self, opt, strikes, vols, n_paths, seed=1234, option_type=CALL):
         n_sets = len(strikes)
         if n_sets > self.max_sets:
-            self._reserve(n_sets)
+            with self.torch.cuda.stream(self.stream):
+                self._reserve(n_sets)
+            self.stream.synchronize()
         self.engine.sweep_segments_async(opt, strikes, vols, n_paths, seed, option_type, self.rank, self.world,
                                          self.segments.data_ptr(), self._stream())
         self._finish_async(n_sets, n_paths, opt.r, opt.T)
@@ -106,9 +156,14 @@ class ShardedPricer:
         self.torch.cuda.current_stream(self.device).synchronize()
         out = (Result * n_sets)()
         C.memmove(out, self.h_results.data_ptr(), C.sizeof(Result) * n_sets)
+        for r in out:
+            if r.n_paths == 0 or r.price != r.price:
+                raise McbError(5, "a sharded result is poisoned (n_paths == 0 / NaN): a rank did not deliver")
         return list(out)
 
     def price_european(self, opt, n_paths, seed=1234, option_type=CALL) -> Result:
+        if self.transport == "peer":
+            return self.engine.european_collect(self.engine.european_submit(opt, n_paths, seed, option_type))
         with self.torch.cuda.stream(self.stream):
             self.european_async(opt, n_paths, seed, option_type)
             return self._fetch(1)[0]

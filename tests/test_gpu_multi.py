@@ -1,6 +1,7 @@
-"""Multi-GPU (NCCL) checks of the sharded path: needs >= 2 B200s (`gpurun --gpus 2`); on a 1-GPU
-box the tests skip and tests/test_dist_gloo.py + test_sharded_segments_bit_identical_for_any_world
-cover the same logic."""
+"""Multi-GPU, one process per GPU (NCCL all-reduce and the CUDA-IPC job pipeline): needs >= 2 B200s
+(`gpurun --gpus 2`); on a 1-GPU box this skips and tests/test_gpu_shards.py (several shards of ONE engine
+on one GPU), tests/test_dist_gloo.py and test_sharded_segments_bit_identical_for_any_world cover the same
+logic; bench.py --gpus N prints the price bits at every N."""
 import os
 import sys
 
@@ -25,7 +26,8 @@ def _worker(rank, world, port, out_dir):
         pkg = entry.load_package()
         sharded = importlib.import_module(entry.PKG_NAME + ".sharded")
         eng = pkg.Engine(rank)
-        pricer = sharded.ShardedPricer(eng)
+        pricer = sharded.ShardedPricer(eng, transport="nccl")
+        assert pricer.transport == "nccl"
         n = 37 * pkg.EUROPEAN_CHUNK + 999
         opt = pkg.option(N_PATHS=n)
         res = pricer.price_european(opt, n, 1234, pkg.CALL)
@@ -48,17 +50,30 @@ def _worker(rank, world, port, out_dir):
         pricer.synchronize()
         assert (lo2, n2) == (lo, hi - lo) and (dev_rows.cpu().numpy().view(np.uint32) == rows.view(np.uint32)).all()
         np.save(os.path.join(out_dir, f"F{rank}.npy"), F.cpu().numpy())
-        # NCCL-free transports: segments all-gathered by NVLink peer stores (CUDA IPC mailboxes), from the
-        # segment pass ("peer") or from inside the pricing kernel itself ("fused", one launch per price)
+        # the job pipeline over CUDA-IPC mailboxes: each rank's pricing kernel stores its segments into every
+        # rank's mailbox over NVLink; ONE pricing launch + one final pass per job, no collective library.
+        # Jobs of >= 64 chunks with a ragged tail (every segment has its own last CTA), 7 epochs so that
+        # the 4-slot ring, the tickets, the flags and the acks are all reused; a second pricer on the SAME
+        # engine re-connects the mailboxes (epochs are agreed at connect time and stay monotonic).
         eng2 = pkg.Engine(rank)
         peer_out = []
-        for transport in ("peer", "fused"):
-            peer = sharded.ShardedPricer(eng2, transport=transport)
-            for k in range(5):   # several epochs: parity buffers, flags and tickets are reused
-                rp = peer.price_european(opt, n + k, 1234, pkg.CALL)
+        n_big = 200 * pkg.EUROPEAN_CHUNK + 999
+        for generation in range(2):
+            peer = sharded.ShardedPricer(eng2, transport="peer")
+            assert peer.transport == "peer"
+            for k in range(7):
+                before = eng2.launch_count
+                rp = peer.price_european(opt, n_big + k, 1234, pkg.CALL)
+                assert eng2.launch_count - before == 2, "one pricing launch + one final pass per job"
                 peer_out += [rp.sum, rp.sumsq, rp.price, float(rp.n_paths)]
-            small = peer.price_european(opt, 100_000, 1234, pkg.PUT)   # < 64 chunks: 3-launch form either way
+            small = peer.price_european(opt, 100_000, 1234, pkg.PUT)   # 7 chunks: most ranks own none
             peer_out += [small.sum, small.sumsq, small.price, float(small.n_paths)]
+            # pipelined: several jobs in flight, collected afterwards
+            tickets = [eng2.european_submit(opt, n_big + 10 + k, 1234, pkg.CALL) for k in range(6)]
+            for t in tickets:
+                rp = eng2.european_collect(t)
+                peer_out += [rp.sum, rp.sumsq]
+        assert eng2.peer_timeouts() == 0
         np.save(os.path.join(out_dir, f"peer{rank}.npy"), np.array(peer_out))
         dist.barrier()
         eng2.close()
@@ -93,12 +108,16 @@ def test_nccl_sharded_prices_match_single_gpu_bits(tmp_path, pkg, engine):
         got_rows.append(np.load(tmp_path / f"rows{r}.npy"))
     assert (np.concatenate(got_rows).view(np.uint32) == rows.view(np.uint32)).all()
     want_peer = []
-    for _transport in ("peer", "fused"):
-        for k in range(5):
-            r1 = engine.price_european(pkg.option(N_PATHS=n + k), n + k, 1234, pkg.CALL)
-            want_peer += [r1.sum, r1.sumsq, r1.price, float(n + k)]
+    n_big = 200 * pkg.EUROPEAN_CHUNK + 999
+    for _generation in range(2):
+        for k in range(7):
+            r1 = engine.price_european(pkg.option(N_PATHS=n_big + k), n_big + k, 1234, pkg.CALL)
+            want_peer += [r1.sum, r1.sumsq, r1.price, float(n_big + k)]
         r2 = engine.price_european(pkg.option(), 100_000, 1234, pkg.PUT)
         want_peer += [r2.sum, r2.sumsq, r2.price, 100_000.0]
+        for k in range(6):
+            r3 = engine.price_european(pkg.option(), n_big + 10 + k, 1234, pkg.CALL)
+            want_peer += [r3.sum, r3.sumsq]
     for r in range(world):
         assert (np.load(tmp_path / f"peer{r}.npy") == np.array(want_peer)).all(), r   # bit-identical, no timeout
     nm = pkg.option(N_STEPS=12, N_PATHS=20, N_PATHS_INNER=128, B=120.0, P1=1, P2=10)

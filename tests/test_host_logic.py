@@ -116,7 +116,7 @@ def test_c_abi_exports_every_declared_symbol(pkg):
     out = subprocess.run(["nm", "-D", "--defined-only", pkg.LIB_PATH], capture_output=True, text=True, check=True)
     exported = set(re.findall(r"\bT (mcb_[a-z0-9_]+)", out.stdout))
     assert set(declared) <= exported
-    assert lib.mcb_version() == 1
+    assert lib.mcb_version() == 2
 
 
 def test_no_device_is_a_loud_error(pkg):
