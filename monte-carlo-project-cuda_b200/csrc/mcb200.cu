@@ -287,6 +287,9 @@ int reserve_results(mcb_engine *e, size_t n)
 
 constexpr uint64_t kEuropeanChunk = (uint64_t)MCB_SLOTS * MCB_EUROPEAN_PATHS_PER_SLOT;
 constexpr uint64_t kBulletChunk = (uint64_t)MCB_SLOTS * MCB_BULLET_PATHS_PER_SLOT;
+// European jobs whose shard has at least this many chunks (2^26 paths, ~0.16 ms) price with the plain
+// kernel + a segment launch instead of the single fused launch (see segments_job_kernel)
+constexpr uint64_t kTwoLaunchChunks = 4096;
 
 uint64_t resolve_paths(const mcb_option_data *o, uint64_t n_paths)
 {
@@ -303,15 +306,60 @@ __global__ void curand_blocks_kernel(uint64_t seed, const uint64_t *__restrict__
     out[i] = curand4(&s);
 }
 
-// One row layout (SPL steps per lane, LPR lanes per row): the TMA slab kernel when the row fits one
+// ---- TMA tensor maps for the fast slab kernel ----------------------------------------------------
+// The driver's encoder is reached through the runtime (no link against libcuda).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn tensor_map_encoder()
+{
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+// The output array seen as [lines][16] 4-byte elements (64-byte lines); a box is one slab.
+bool encode_slab_map(CUtensorMap *map, void *base, uint64_t total_elems, uint32_t slab_elems, bool is_int)
+{
+    EncodeTiledFn enc = tensor_map_encoder();
+    if (!enc || !base) return false;
+    const cuuint64_t dims[2] = {16, total_elems / 16};
+    const cuuint64_t strides[1] = {64};
+    const cuuint32_t box[2] = {16, slab_elems / 16};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(map, is_int ? CU_TENSOR_MAP_DATA_TYPE_INT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box,
+               estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// Tuning knobs of the trajectory launcher (tools/traj_bench.py sweeps them through the environment;
+// unset = the shipped configuration).
+int env_int(const char *name, int dflt)
+{
+    const char *v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
+// One row layout (SPL steps per lane, LPR lanes per row): the TMA slab kernels when the row fits one
 // pass and is 16-byte aligned (the bandwidth path, config 3; counts and log2 prices ride along in
 // their own staging rows), the general kernel otherwise.
 template <int SPL, int LPR>
-void launch_trajectory(const PathParams &prm, uint64_t n_paths, bool vec, bool base_aligned, float *d_prices,
+void launch_trajectory(const PathParams &prm_in, uint64_t n_paths, bool vec, bool base_aligned, float *d_prices,
                        int *d_counts, float *d_logs, cudaStream_t st)
 {
     constexpr int kRowsPerWarp = 32 / LPR;
     constexpr int kSlabWarps = 4;
+    PathParams prm = prm_in;
+    SlabTensorMaps maps{};
     // rows longer than one pass: one row group per slab, the whole rows staged -- while the staging
     // leaves enough CTAs per SM (measured on 2^20 rows: prices only 4.07 TB/s at 1024 steps / 32 KB,
     // 3.67 at 1536 / 48 KB, then the general kernel's 3.5 TB/s wins; with counts the general
@@ -319,16 +367,18 @@ void launch_trajectory(const PathParams &prm, uint64_t n_paths, bool vec, bool b
     // rows take the general kernel
     const int n_arrays = 1 + (d_counts ? 1 : 0) + (d_logs ? 1 : 0);
     const size_t multi_smem = (size_t)kSlabWarps * n_arrays * kRowsPerWarp * (size_t)prm.n_steps * sizeof(float);
-#define MCB_SLAB(ROWS, CNT, LOG, MULTI, ALIGNED)                                                              \
+#define MCB_SLAB_W(ROWS, CNT, LOG, MULTI, ALIGNED, FAST, WARPS)                                               \
     do {                                                                                                      \
-        auto kern = trajectory_slab_kernel<SPL, LPR, ROWS, kSlabWarps, CNT, LOG, MULTI, ALIGNED>;             \
-        const uint64_t rows_per_cta = (uint64_t)kSlabWarps * ROWS;                                            \
-        const uint64_t ctas = (n_paths + rows_per_cta - 1) / rows_per_cta;                                    \
-        const size_t smem = (size_t)kSlabWarps * (1 + (CNT ? 1 : 0) + (LOG ? 1 : 0)) * ROWS *                 \
-                            (size_t)prm.n_steps * sizeof(float);                                              \
+        auto kern = trajectory_slab_kernel<SPL, LPR, ROWS, WARPS, CNT, LOG, MULTI, ALIGNED, FAST>;            \
+        const uint64_t rows_per_cta = (uint64_t)(WARPS) * (ROWS);                                             \
+        const uint64_t ctas = (prm.n_paths + rows_per_cta - 1) / rows_per_cta;                                \
+        const size_t per_array = (FAST) ? ((((size_t)(ROWS) * (size_t)prm.n_steps + 127) & ~(size_t)127))     \
+                                        : (size_t)(ROWS) * (size_t)prm.n_steps;                               \
+        const size_t smem = (size_t)(WARPS) * (1 + (CNT ? 1 : 0) + (LOG ? 1 : 0)) * per_array * sizeof(float); \
         if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        kern<<<(unsigned)ctas, kSlabWarps * 32, smem, st>>>(prm, d_prices, d_counts, d_logs);                 \
+        kern<<<(unsigned)ctas, (WARPS) * 32, smem, st>>>(prm, d_prices, d_counts, d_logs, maps);              \
     } while (0)
+#define MCB_SLAB(ROWS, CNT, LOG, MULTI, ALIGNED) MCB_SLAB_W(ROWS, CNT, LOG, MULTI, ALIGNED, false, kSlabWarps)
     // (only the largest layout is ever asked for rows longer than its pass)
     if (SPL * LPR == 256 && vec && prm.n_steps > SPL * LPR && multi_smem <= (n_arrays == 1 ? 48 : 72) * 1024) {
         if constexpr (SPL * LPR == 256) {
@@ -338,12 +388,47 @@ void launch_trajectory(const PathParams &prm, uint64_t n_paths, bool vec, bool b
             else MCB_SLAB(kRowsPerWarp, false, false, true, true);
         }
     } else if (vec && prm.n_steps <= SPL * LPR) {
+        // The fast variant (hoisted Philox products, packed FP32x2, swizzled staging + one TMA tensor
+        // store per array) takes every whole slab of 4 rows (4 * n_steps floats are whole 64-byte lines
+        // because n_steps % 4 == 0); a ragged tail of up to 3 rows goes to the linear slab kernel below.
+        constexpr int kFastRows = 4;
+        static_assert(kFastRows % kRowsPerWarp == 0, "a slab is a whole number of passes");
+        const uint64_t fast_paths = n_paths / kFastRows * kFastRows;
+        const uint64_t total = fast_paths * (uint64_t)prm.n_steps;
+        const int mode = env_int("MCB_TRAJ_MODE", 1);   // 0: linear slab kernel only (round-1 path)
+        bool fast = mode != 0 && fast_paths > 0 && total / 16 < 0x7fffffffull;
+        if (fast) fast = encode_slab_map(&maps.prices, d_prices, total, kFastRows * (uint32_t)prm.n_steps, false);
+        if (fast && d_counts) fast = encode_slab_map(&maps.counts, d_counts, total, kFastRows * (uint32_t)prm.n_steps, true);
+        if (fast && d_logs) fast = encode_slab_map(&maps.logs, d_logs, total, kFastRows * (uint32_t)prm.n_steps, false);
+        if (fast) {
+            prm.n_paths = fast_paths;
+            const int warps = env_int("MCB_TRAJ_WARPS", 4);
+#define MCB_FAST(WARPS)                                                                                        \
+            do {                                                                                               \
+                if (d_counts && d_logs) MCB_SLAB_W(kFastRows, true, true, false, true, true, WARPS);           \
+                else if (d_counts) MCB_SLAB_W(kFastRows, true, false, false, true, true, WARPS);               \
+                else if (d_logs) MCB_SLAB_W(kFastRows, false, true, false, true, true, WARPS);                 \
+                else MCB_SLAB_W(kFastRows, false, false, false, true, true, WARPS);                            \
+            } while (0)
+            if (warps == 8) MCB_FAST(8);
+            else if (warps == 2) MCB_FAST(2);
+            else MCB_FAST(4);
+#undef MCB_FAST
+            // the tail: rows [fast_paths, n_paths) through the linear kernel
+            prm.first_path = prm_in.first_path + fast_paths;
+            prm.n_paths = n_paths - fast_paths;
+            const uint64_t off = fast_paths * (uint64_t)prm.n_steps;
+            d_prices += off;
+            if (d_counts) d_counts += off;
+            if (d_logs) d_logs += off;
+        }
         // rows per slab: ~6 for one output array (tuned on B200 at 2^20 x 252, profiles/r1_trajectory_tuning.txt),
         // fewer when counts / logs need their own staging rows; always a whole number of passes
         constexpr int kRows1 = (6 + kRowsPerWarp - 1) / kRowsPerWarp * kRowsPerWarp;
         constexpr int kRows2 = (4 + kRowsPerWarp - 1) / kRowsPerWarp * kRowsPerWarp;
         constexpr int kRows3 = (2 + kRowsPerWarp - 1) / kRowsPerWarp * kRowsPerWarp;
-        if (d_counts && d_logs) MCB_SLAB(kRows3, true, true, false, true);
+        if (prm.n_paths == 0) {
+        } else if (d_counts && d_logs) MCB_SLAB(kRows3, true, true, false, true);
         else if (d_counts) MCB_SLAB(kRows2, true, false, false, true);
         else if (d_logs) MCB_SLAB(kRows2, false, true, false, true);
         else MCB_SLAB(kRows1, false, false, false, true);
@@ -355,6 +440,7 @@ void launch_trajectory(const PathParams &prm, uint64_t n_paths, bool vec, bool b
         else if (d_logs) MCB_SLAB(4, false, true, false, false);
         else MCB_SLAB(8, false, false, false, false);
 #undef MCB_SLAB
+#undef MCB_SLAB_W
     } else {
         const uint64_t rows_per_cta = (uint64_t)kPathWarps * kPathsPerWarp * kRowsPerWarp;
         const unsigned g = (unsigned)((n_paths + rows_per_cta - 1) / rows_per_cta), b = kPathWarps * 32;
@@ -711,7 +797,14 @@ int submit_shard(mcb_engine *s, mcb_engine *L, const mcb_option_data *opt, uint6
         args.h_out = &s->h_ring[epoch % kHostRing];
         args.h_segments = s->h_segments;
     }
-    if (c_hi > c_lo) {
+    if (c_hi - c_lo >= kTwoLaunchChunks) {
+        // large shard: the plain pricing kernel, then one CTA per owned segment (see segments_job_kernel)
+        const EuropeanParams prm = european_params(opt, opt->K, opt->v, n_paths, seed, c_lo);
+        if ((rc = launch_european<MCB_EUROPEAN_PATHS_PER_SLOT>(s, prm, option_type, c_hi - c_lo, s->partials.ptr,
+                                                               nullptr, 0, s->stream)))
+            return rc;
+        segments_job_kernel<<<(unsigned)(seg_hi - seg_lo), kSlots, 0, s->stream>>>(args, s->partials.ptr, c_lo);
+    } else if (c_hi > c_lo) {
         const EuropeanParams prm = european_params(opt, opt->K, opt->v, n_paths, seed, c_lo);
         TimedScope timed(s, MCB_KERNEL_EUROPEAN, s->stream);
         if (option_type == MCB_PUT)

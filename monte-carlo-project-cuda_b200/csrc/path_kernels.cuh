@@ -6,6 +6,7 @@
 //   compute_nmc_one_block_per_point / _with_outter / compute_nmc_optimal   inc/nmc.cuh:12-386
 #pragma once
 #include <cstdint>
+#include <cuda.h>   // CUtensorMap (type only; the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cuda_runtime.h>
 
 #include "block_reduce.cuh"
@@ -133,13 +134,68 @@ __device__ __forceinline__ PassWords<SPL> row_words(const PathParams &prm, uint3
     return out;
 }
 
-// floating-point half: Box-Muller -> log2 increments -> in-lane prefix -> scan over the row's lanes
-template <int SPL, int LPR>
+// The first two Philox rounds of a trajectory block depend on far less than (lane, row): the
+// counter is (block, 0, p_lo, p_hi), so
+//   round 0:  M0 * block   -- a function of the LANE only (its blocks are the same for every row),
+//             M1 * p_lo    -- a function of the ROW only (the same for the lane's SPL/4 blocks);
+//   round 1:  M0 * (hi(M1 p_lo) ^ k0[0])            -- row only,
+//             M1 * (hi(M0 block) ^ p_hi ^ k1[0])    -- lane only, as long as p_hi does not change.
+// RowHoist keeps the lane-only products (three words per block) in registers for the whole kernel;
+// a row then costs two multiplies for all its blocks and each block enters round 2 after two XORs:
+// 16.5 instead of 20 IMAD.WIDE per block, the same words bit for bit.
+template <int SPL>
+struct RowHoist {
+    uint32_t a[SPL / 4];   // hi(M1 * c2') ^ k0[1]
+    uint32_t b[SPL / 4];   // lo(M1 * c2')
+    uint32_t d[SPL / 4];   // lo(M0 * block) ^ k1[1]
+    uint32_t p_hi;         // the high path word the products were formed with
+};
+
+template <int SPL>
+__device__ __forceinline__ RowHoist<SPL> make_row_hoist(const PathParams &prm, uint32_t p_hi, int my_step)
+{
+    RowHoist<SPL> h;
+    h.p_hi = p_hi;
+#pragma unroll
+    for (int j = 0; j < SPL / 4; ++j) {
+        const uint64_t p0 = (uint64_t)kPhiloxM0 * ((uint32_t)(my_step >> 2) + (uint32_t)j);
+        const uint32_t c2 = (uint32_t)(p0 >> 32) ^ p_hi ^ prm.keys.k1[0];
+        const uint64_t p1 = (uint64_t)kPhiloxM1 * c2;
+        h.a[j] = (uint32_t)(p1 >> 32) ^ prm.keys.k0[1];
+        h.b[j] = (uint32_t)p1;
+        h.d[j] = (uint32_t)p0 ^ prm.keys.k1[1];
+    }
+    return h;
+}
+
+// == row_words(prm, p_lo, h.p_hi, my_step) for the my_step the hoist was made with
+template <int SPL>
+__device__ __forceinline__ PassWords<SPL> row_words_hoisted(const PathParams &prm, const RowHoist<SPL> &h, uint32_t p_lo)
+{
+    const uint64_t q1 = (uint64_t)kPhiloxM1 * p_lo;                                   // round 0, row part
+    const uint64_t q0 = (uint64_t)kPhiloxM0 * ((uint32_t)(q1 >> 32) ^ prm.keys.k0[0]);  // round 1, row part
+    PassWords<SPL> out;
+#pragma unroll
+    for (int j = 0; j < SPL / 4; ++j) {
+        uint32_t c0 = h.a[j] ^ (uint32_t)q1, c1 = h.b[j], c2 = (uint32_t)(q0 >> 32) ^ h.d[j], c3 = (uint32_t)q0;
+#pragma unroll
+        for (int r = 2; r < 10; ++r) philox_round(c0, c1, c2, c3, prm.keys.k0[r], prm.keys.k1[r]);
+        out.w[j] = Words4{c0, c1, c2, c3};
+    }
+    return out;
+}
+
+// floating-point half: Box-Muller -> log2 increments -> in-lane prefix -> scan over the row's lanes.
+// PACK: the Box-Muller arithmetic in FP32x2 instructions (philox.cuh) -- fewer issue slots, same bits.
+template <int SPL, int LPR, bool PACK = false>
 __device__ __forceinline__ float row_finish(const PathParams &prm, const PassWords<SPL> &words, bool active,
                                             float &carry_l, float (&a)[SPL])
 {
 #pragma unroll
-    for (int b = 0; b < SPL / 4; ++b) increments4(words.w[b], prm.sc, prm.dr, a + 4 * b);
+    for (int b = 0; b < SPL / 4; ++b) {
+        if (PACK) increments4_packed(words.w[b], prm.sc, prm.dr, a + 4 * b);
+        else increments4(words.w[b], prm.sc, prm.dr, a + 4 * b);
+    }
 #pragma unroll
     for (int j = 1; j < SPL; ++j) a[j] = a[j] + a[j - 1];
     // lanes past the end of the row computed garbage (branch-free, the warp stays converged for
@@ -263,17 +319,39 @@ trajectory_kernel(const __grid_constant__ PathParams prm, float *__restrict__ pr
 // Otherwise (150- or 250-step rows ...) the lanes stage element by element, ROWS is a multiple
 // of 4 so that every SLAB still starts on a 16-byte boundary of the output, the bulk store takes
 // the slab's whole 16-byte units and one lane writes the last one to three floats of a ragged slab.
-template <int SPL, int LPR, int ROWS, int WARPS, bool COUNTS, bool LOGS, bool MULTI = false, bool ALIGNED = true>
+// FAST (one-pass, 16-byte aligned rows only): the three issue-slot savers together --
+//   * the lane-invariant Philox products hoisted out of the row loop (RowHoist),
+//   * Box-Muller and the base add in packed FP32x2 instructions,
+//   * conflict-free staging: the lanes' STS.128 at a 64-byte lane stride hit two bank groups (4-way
+//     conflict, 70 % of the kernel's shared-memory wavefronts, which queue in the same MIO pipe the
+//     MUFU instructions need); the slab is staged with TMA's 64-byte swizzle (address bits 4-5 ^= bits
+//     7-8: every quarter-warp then covers all eight 16-byte bank groups) and leaves through ONE
+//     cp.async.bulk.tensor store per array that un-swizzles on the way out.  The output is described to
+//     TMA as a [total/16][16] float tensor, so slabs only need to be whole 64-byte lines:
+//     ROWS * n_steps % 16 == 0 (the host picks ROWS and sends a ragged tail to the linear kernel).
+struct SlabTensorMaps {
+    CUtensorMap prices, counts, logs;
+};
+
+__device__ __forceinline__ void tensor_store_2d(void *smem, const CUtensorMap *map, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 :: "l"(map), "r"(smem_addr(smem)), "r"(c0), "r"(c1) : "memory");
+}
+
+template <int SPL, int LPR, int ROWS, int WARPS, bool COUNTS, bool LOGS, bool MULTI = false, bool ALIGNED = true,
+          bool FAST = false>
 __global__ void __launch_bounds__(WARPS * 32)
 trajectory_slab_kernel(const __grid_constant__ PathParams prm, float *__restrict__ prices, int *__restrict__ counts,
-                       float *__restrict__ logs)
+                       float *__restrict__ logs, const __grid_constant__ SlabTensorMaps maps)
 {
+    static_assert(!FAST || (ALIGNED && !MULTI), "the fast path is for one-pass, 16-byte aligned rows");
     constexpr int kBlocks = SPL / 4;
     constexpr int kRowsPerWarp = 32 / LPR;
     constexpr int kArrays = 1 + (COUNTS ? 1 : 0) + (LOGS ? 1 : 0);
     static_assert(ROWS % kRowsPerWarp == 0, "a slab is a whole number of passes");
     static_assert(ALIGNED || ROWS % 4 == 0, "unaligned rows: slabs must start on 16-byte boundaries");
-    extern __shared__ __align__(128) float stage[];    // [warp][array][ROWS][n_steps]
+    extern __shared__ __align__(1024) float stage[];   // [warp][array][ROWS][n_steps] (FAST: each array 512-byte aligned)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sub = lane / LPR, ln = lane % LPR;
     const int n_steps = prm.n_steps;
@@ -281,9 +359,12 @@ trajectory_slab_kernel(const __grid_constant__ PathParams prm, float *__restrict
     const uint32_t n_slabs = (n_rows + ROWS - 1) / ROWS;
     const uint32_t slab_stride = gridDim.x * WARPS;   // a warp strides over the slabs (one each when the grid covers them)
     const int lane_step = SPL * ln;
-    const int slab_floats = ROWS * n_steps;
+    // floats between the arrays of a slab in shared memory: dense, or rounded up to the swizzle period
+    const int slab_floats = FAST ? ((ROWS * n_steps + 127) & ~127) : ROWS * n_steps;
     float *my_stage = stage + (size_t)warp * kArrays * slab_floats;
     float *dst0 = my_stage + sub * n_steps + lane_step;
+    RowHoist<SPL> hoist;
+    if (FAST) hoist = make_row_hoist<SPL>(prm, (uint32_t)(prm.first_path >> 32), lane_step);
 
 #pragma unroll 1
     for (uint32_t slab = blockIdx.x * WARPS + warp; slab < n_slabs; slab += slab_stride) {
@@ -301,11 +382,19 @@ trajectory_slab_kernel(const __grid_constant__ PathParams prm, float *__restrict
             for (int step0 = 0; step0 < (MULTI ? n_steps : 1); step0 += SPL * LPR) {
                 const int my_step = step0 + lane_step;
                 const bool active = my_step < n_steps;
-                const PassWords<SPL> words = row_words<SPL>(prm, (uint32_t)p, (uint32_t)(p >> 32), my_step);
+                PassWords<SPL> words;
+                if (FAST && (uint32_t)(p >> 32) == hoist.p_hi) words = row_words_hoisted<SPL>(prm, hoist, (uint32_t)p);
+                else words = row_words<SPL>(prm, (uint32_t)p, (uint32_t)(p >> 32), my_step);
                 float a[SPL];
-                const float base = row_finish<SPL, LPR>(prm, words, active, carry_l, a);
+                const float base = row_finish<SPL, LPR, FAST>(prm, words, active, carry_l, a);
+                if (FAST) {                                                  // log2 prices of this lane's steps
+                    const uint64_t bb = f2_pack(base, base);
 #pragma unroll
-                for (int j = 0; j < SPL; ++j) a[j] = base + a[j];          // log2 prices of this lane's steps
+                    for (int j = 0; j < SPL; j += 2) f2_unpack(f2_add(f2_pack(a[j], a[j + 1]), bb), a[j], a[j + 1]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < SPL; ++j) a[j] = base + a[j];
+                }
                 int cbase = carry_c;
                 if (COUNTS) {
                     int run = 0;
@@ -333,7 +422,16 @@ trajectory_slab_kernel(const __grid_constant__ PathParams prm, float *__restrict
                                 c[j] = cbase;
                             }
                         }
-                        if (ALIGNED) {
+                        if (FAST) {
+                            // 64-byte swizzle on the slab-linear offset: 16-byte unit index ^= (offset >> 7) & 3
+                            const uint32_t lin = (uint32_t)((r + sub) * n_steps + lane_step + 4 * b) * 4u;
+                            float *sw = my_stage + ((lin ^ ((lin >> 3) & 0x30u)) >> 2);
+                            if (COUNTS) *reinterpret_cast<int4 *>(sw + slab_floats) = make_int4(c[0], c[1], c[2], c[3]);
+                            if (LOGS)
+                                *reinterpret_cast<float4 *>(sw + (COUNTS ? 2 : 1) * slab_floats) =
+                                    make_float4(a[4 * b], a[4 * b + 1], a[4 * b + 2], a[4 * b + 3]);
+                            *reinterpret_cast<float4 *>(sw) = make_float4(s4[0], s4[1], s4[2], s4[3]);
+                        } else if (ALIGNED) {
                             if (COUNTS)
                                 *reinterpret_cast<int4 *>(dst + slab_floats + 4 * b) = make_int4(c[0], c[1], c[2], c[3]);
                             if (LOGS)
@@ -356,7 +454,16 @@ trajectory_slab_kernel(const __grid_constant__ PathParams prm, float *__restrict
         }
         fence_async_smem();   // generic-proxy STS -> visible to the async proxy (TMA)
         __syncwarp();
-        if (lane == 0) {
+        if (FAST) {
+            // the host launches this variant on whole slabs only; ONE tensor store per array un-swizzles
+            if (lane == 0) {
+                const int line = (int)(((uint64_t)slab_row * (uint32_t)n_steps) >> 4);   // 64-byte line of the slab
+                tensor_store_2d(my_stage, &maps.prices, 0, line);
+                if (COUNTS) tensor_store_2d(my_stage + slab_floats, &maps.counts, 0, line);
+                if (LOGS) tensor_store_2d(my_stage + (COUNTS ? 2 : 1) * slab_floats, &maps.logs, 0, line);
+                bulk_commit();
+            }
+        } else if (lane == 0) {
             const uint32_t rows = min((uint32_t)ROWS, n_rows - slab_row);
             const uint32_t floats = rows * (uint32_t)n_steps;
             const uint32_t bytes = ALIGNED ? floats * 4u : (floats * 4u) & ~15u;   // whole 16-byte units

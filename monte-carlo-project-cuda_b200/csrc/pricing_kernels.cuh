@@ -523,24 +523,13 @@ __device__ __forceinline__ void final_tree_warp(const volatile double *seg, int 
     }
 }
 
-__device__ __noinline__ void job_tail(const JobArgs &args, const float2 *__restrict__ partials, uint64_t first_chunk,
-                                      double *dscratch, int *flag)
+// Fold segment `seg` of this shard (all kSlots threads, same order as segment_kernel), store it into
+// every consumer's mailbox slot, and -- in the CTA that completes the shard's last segment -- write
+// the empty segments, publish the flag and (world == 1) run the final tree.
+__device__ __forceinline__ void job_fold_and_publish(const JobArgs &args, const float2 *__restrict__ partials,
+                                                     uint64_t first_chunk, int seg, double *dscratch, int *flag)
 {
-    const uint64_t chunk = first_chunk + blockIdx.x;
     const uint64_t n = args.n_chunks;
-    if (threadIdx.x == 0) {
-        __threadfence();                                    // my partial is visible device-wide
-        int seg = (int)((chunk * (uint64_t)kSegments) / n);
-        while ((n * (uint64_t)(seg + 1)) / kSegments <= chunk) ++seg;
-        while ((n * (uint64_t)seg) / kSegments > chunk) --seg;
-        const uint64_t lo = (n * (uint64_t)seg) / kSegments, hi = (n * (uint64_t)(seg + 1)) / kSegments;
-        const unsigned int t = atomicAdd(&args.seg_tickets[seg], 1u);
-        flag[0] = (t == (unsigned int)(hi - lo) - 1u) ? seg : -1;
-    }
-    __syncthreads();
-    const int seg = flag[0];
-    if (seg < 0) return;                                    // CTA-uniform: not the last chunk of its segment
-    __threadfence();
     const uint64_t lo = (n * (uint64_t)seg) / kSegments, hi = (n * (uint64_t)(seg + 1)) / kSegments;
     double a = 0.0, b = 0.0;
     for (uint64_t c = lo + threadIdx.x; c < hi; c += kSlots) {
@@ -552,7 +541,6 @@ __device__ __noinline__ void job_tail(const JobArgs &args, const float2 *__restr
     const int slot = (int)(args.epoch % (unsigned long long)kRing);
     PeerMailbox *mine = args.peers.box[args.rank];
     if (threadIdx.x == 0) {
-        args.seg_tickets[seg] = 0u;                         // ready for the next launch
         for (int c = 0; c < args.n_consumers; ++c) {
             // the slot still holds job epoch - kRing until consumer c has folded it
             if (args.check_acks && args.epoch > (unsigned long long)kRing &&
@@ -584,7 +572,7 @@ __device__ __noinline__ void job_tail(const JobArgs &args, const float2 *__restr
         if (args.world > 1) __threadfence_system(); else __threadfence();
         __syncthreads();
     }
-    if (threadIdx.x == 0) args.seg_tickets[kSegments] = 0u;
+    if (threadIdx.x == 0) args.seg_tickets[kSegments] = 0u;   // ready for the next launch
     if (args.world > 1) {
         if (threadIdx.x < (unsigned)args.n_consumers)
             *((volatile unsigned long long *)&args.peers.box[threadIdx.x]->flags[slot][args.rank]) = args.epoch;
@@ -599,6 +587,44 @@ __device__ __noinline__ void job_tail(const JobArgs &args, const float2 *__restr
         if (args.h_segments) __threadfence_system();
         final_tree_warp(sg, (int)threadIdx.x, args.n_paths, args.discount, true, args.epoch, args.d_out, args.h_out);
     }
+}
+
+// Tail of european_job_kernel: a ticket per segment finds the last CTA of each.
+__device__ __noinline__ void job_tail(const JobArgs &args, const float2 *__restrict__ partials, uint64_t first_chunk,
+                                      double *dscratch, int *flag)
+{
+    const uint64_t chunk = first_chunk + blockIdx.x;
+    const uint64_t n = args.n_chunks;
+    if (threadIdx.x == 0) {
+        __threadfence();                                    // my partial is visible device-wide
+        int seg = (int)((chunk * (uint64_t)kSegments) / n);
+        while ((n * (uint64_t)(seg + 1)) / kSegments <= chunk) ++seg;
+        while ((n * (uint64_t)seg) / kSegments > chunk) --seg;
+        const uint64_t lo = (n * (uint64_t)seg) / kSegments, hi = (n * (uint64_t)(seg + 1)) / kSegments;
+        const unsigned int t = atomicAdd(&args.seg_tickets[seg], 1u);
+        flag[0] = (t == (unsigned int)(hi - lo) - 1u) ? seg : -1;
+        if (flag[0] >= 0) args.seg_tickets[seg] = 0u;       // ready for the next launch
+    }
+    __syncthreads();
+    const int seg = flag[0];
+    if (seg < 0) return;                                    // CTA-uniform: not the last chunk of its segment
+    __threadfence();
+    job_fold_and_publish(args, partials, first_chunk, seg, dscratch, flag);
+}
+
+// Large shards: the per-CTA ticket of european_job_kernel holds every CTA's slot for one L2 round
+// trip (~0.8 us of 45 us, measured 1.8 % at 2^30 paths), more than a second launch costs once the
+// shard runs for ~0.3 ms.  Those jobs price with the plain european_kernel and fold here: one CTA per
+// owned segment, then exactly the same publish / final-tree tail.
+__global__ void __launch_bounds__(kSlots)
+segments_job_kernel(const __grid_constant__ JobArgs args, const float2 *__restrict__ partials, uint64_t first_chunk)
+{
+    __shared__ double dscratch[2 * kWarps];
+    __shared__ int flag[2];
+    const int seg = args.seg_lo + (int)blockIdx.x;
+    const uint64_t n = args.n_chunks;
+    if ((n * (uint64_t)seg) / kSegments == (n * (uint64_t)(seg + 1)) / kSegments) return;   // no chunk: CTA-uniform
+    job_fold_and_publish(args, partials, first_chunk, seg, dscratch, flag);
 }
 
 template <int TYPE, int PPS>

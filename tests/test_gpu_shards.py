@@ -58,6 +58,33 @@ def test_single_engine_prices_in_one_launch(pkg, engine, orc):
         assert (orc.segment_tree_f64(cp) == seg).all()
 
 
+def test_large_shards_take_the_two_launch_route_with_the_same_bits(pkg, engine, multi_engines):
+    """A shard of >= 4096 chunks prices with the plain kernel + one segment launch (the per-CTA ticket of
+    the fused kernel costs more than a launch there); smaller shards use the single fused launch.  Same
+    tree, same bits: the job below is two-launch on one device and fused on two or more shards."""
+    n = 4100 * pkg.EUROPEAN_CHUNK + 999
+    opt = pkg.option(N_PATHS=1)
+    before = engine.launch_count
+    want = engine.price_european(opt, n, 1234, pkg.CALL)
+    assert engine.launch_count - before == 2
+    seg = engine.last_segments()
+    cp = engine.european_chunk_partials(opt, n, 1234, pkg.CALL)
+    import oracle
+    assert (oracle.segment_tree_f64(cp) == seg).all()
+    assert oracle.final_tree_f64(seg) == (want.sum, want.sumsq)
+    for multi in multi_engines:
+        before = multi.launch_count
+        got = multi.price_european(opt, n, 1234, pkg.CALL)
+        assert multi.launch_count - before == multi.shard_count + 1
+        assert _bits(got) == _bits(want)
+    big = 2 * 4096 * pkg.EUROPEAN_CHUNK + 5          # two shards of 4096 chunks: two-launch on each
+    two = multi_engines[0]
+    before = two.launch_count
+    got = two.price_european(opt, big, 1234, pkg.PUT)
+    assert two.launch_count - before == 2 * 2 + 1
+    assert _bits(got) == _bits(engine.price_european(opt, big, 1234, pkg.PUT))
+
+
 def test_multi_engine_european_bits(pkg, engine, multi_engines):
     sizes = (100_000,                                   # 7 chunks: most shards own nothing, most segments are empty
              63 * pkg.EUROPEAN_CHUNK + 5,               # fewer chunks than segments

@@ -10,22 +10,30 @@
 constexpr int kIters = 2048;
 constexpr int kIlp = 8;
 
-enum Mix { IMADW, LOP3, FFMA, EX2, LG2, SIN, SQRT, IMADW_LOP3, PHILOX_ROUND, FFMA_LOP3, FFMA_IMADW, I2F, FMNMX, MIX_COUNT };
+enum Mix { IMADW, LOP3, FFMA, EX2, LG2, SIN, SQRT, IMADW_LOP3, PHILOX_ROUND, FFMA_LOP3, FFMA_IMADW, I2F, FMNMX,
+           IMAD_HI, IMAD_LO, FFMA2, FFMA2_IMADW, EX2_IMADW, FADD2, FFMA2_LOP3, EX2_FFMA2, MIX_COUNT };
 const char *kNames[] = {"imad.wide.u32", "lop3", "ffma", "mufu.ex2", "mufu.lg2", "mufu.sin(+fmul.rz)", "mufu.sqrt",
                         "imad.wide+lop3 (1:1)", "philox round (2 imad.wide + 2 lop3)", "ffma+lop3 (1:1)",
-                        "ffma+imad.wide (1:1)", "i2fp.u32", "fmnmx"};
-const int kInstrPerStep[] = {1, 1, 1, 1, 1, 2, 1, 2, 4, 2, 2, 1, 1};
+                        "ffma+imad.wide (1:1)", "i2fp.u32", "fmnmx", "imad.hi.u32", "imad (lo)", "ffma2 (packed f32x2)",
+                        "ffma2+imad.wide (1:1)", "mufu.ex2+imad.wide (1:1)", "fadd2", "ffma2+lop3 (1:1)",
+                        "mufu.ex2+ffma2 (1:1)"};
+const int kInstrPerStep[] = {1, 1, 1, 1, 1, 2, 1, 2, 4, 2, 2, 1, 1, 1, 1, 1, 2, 2, 1, 2, 2};
 
 template <int MIX>
 __global__ void __launch_bounds__(1024) bench(uint32_t seed, uint32_t *out, long long *cycles)
 {
     uint32_t a[kIlp], b[kIlp];
     float f[kIlp];
+    unsigned long long g[kIlp];   // packed f32x2 chains
+    unsigned long long gm, ga;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(gm) : "f"(0.999f), "f"(0.998f));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ga) : "f"(1e-3f), "f"(2e-3f));
 #pragma unroll
     for (int j = 0; j < kIlp; ++j) {
         a[j] = seed + threadIdx.x * 7 + j;
         b[j] = seed * 3 + threadIdx.x + j * 5;
         f[j] = 1.0f + 1e-3f * (float)(threadIdx.x + j);
+        asm("mov.b64 %0, {%1, %2};" : "=l"(g[j]) : "f"(f[j]), "f"(f[j] + 0.5f));
     }
     __syncthreads();
     const long long t0 = clock64();
@@ -79,13 +87,35 @@ __global__ void __launch_bounds__(1024) bench(uint32_t seed, uint32_t *out, long
                 a[j] = __float_as_uint(t);
             } else if (MIX == FMNMX) {
                 asm volatile("max.f32 %0, %0, %1;" : "+f"(f[j]) : "f"(__uint_as_float(b[j])));
+            } else if (MIX == IMAD_HI) {
+                asm volatile("mul.hi.u32 %0, %0, %1;" : "+r"(a[j]) : "r"(0xD2511F53u));
+            } else if (MIX == IMAD_LO) {
+                asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[j]) : "r"(0xD2511F53u), "r"(b[j]));
+            } else if (MIX == FFMA2 || MIX == FFMA2_IMADW || MIX == FFMA2_LOP3 || MIX == EX2_FFMA2) {
+                asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(g[j]) : "l"(gm), "l"(ga));
+                if (MIX == FFMA2_IMADW) {
+                    uint64_t p;
+                    asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(p) : "r"(a[j]), "r"(0xD2511F53u));
+                    asm volatile("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(a[j]) : "r"((uint32_t)(p >> 32)), "r"((uint32_t)p), "r"(0u));
+                } else if (MIX == FFMA2_LOP3) {
+                    asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[j]) : "r"(b[j]), "r"(seed));
+                } else if (MIX == EX2_FFMA2) {
+                    asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(f[j]));
+                }
+            } else if (MIX == EX2_IMADW) {
+                uint64_t p;
+                asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(f[j]));
+                asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(p) : "r"(a[j]), "r"(0xD2511F53u));
+                a[j] = (uint32_t)(p >> 32) ^ (uint32_t)p;
+            } else if (MIX == FADD2) {
+                asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(g[j]) : "l"(ga));
             }
         }
     }
     const long long t1 = clock64();
     uint32_t acc = 0;
 #pragma unroll
-    for (int j = 0; j < kIlp; ++j) acc ^= a[j] ^ b[j] ^ __float_as_uint(f[j]);
+    for (int j = 0; j < kIlp; ++j) acc ^= a[j] ^ b[j] ^ __float_as_uint(f[j]) ^ (uint32_t)g[j] ^ (uint32_t)(g[j] >> 32);
     out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
     if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
 }
@@ -128,6 +158,14 @@ int main()
     run<FFMA_IMADW>(sms, out, cycles);
     run<I2F>(sms, out, cycles);
     run<FMNMX>(sms, out, cycles);
+    run<IMAD_HI>(sms, out, cycles);
+    run<IMAD_LO>(sms, out, cycles);
+    run<FFMA2>(sms, out, cycles);
+    run<FFMA2_IMADW>(sms, out, cycles);
+    run<EX2_IMADW>(sms, out, cycles);
+    run<FADD2>(sms, out, cycles);
+    run<FFMA2_LOP3>(sms, out, cycles);
+    run<EX2_FFMA2>(sms, out, cycles);
     cudaError_t err = cudaDeviceSynchronize();
     printf("status: %s\n", cudaGetErrorString(err));
     return err != cudaSuccess;

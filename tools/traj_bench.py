@@ -1,25 +1,61 @@
-"""Times trajectory_kernel (2^20 x 252, device buffer) with CUDA events: python tools/traj_bench.py [steps] [counts]"""
-import os, sys
+"""Times the trajectory kernels (2^20 rows, device buffer) with CUDA events and checks that every launcher
+variant writes the same bits:  python tools/traj_bench.py [steps ...]   (default 252)
+
+Variants are selected through the launcher's environment knobs (csrc/mcb200.cu launch_trajectory):
+MCB_TRAJ_MODE=0 the linear slab kernel (round 1), =1 the fast kernel (hoisted Philox products, packed
+FP32x2, swizzled staging + TMA tensor store); MCB_TRAJ_WARPS = warps per CTA of the fast kernel."""
+import os
+import sys
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
 import __graft_entry__ as entry
+
 pkg = entry.load_package()
-steps = int(sys.argv[1]) if len(sys.argv) > 1 else 252
-want_counts = len(sys.argv) > 2 and sys.argv[2] == "1"
+steps_list = [int(a) for a in sys.argv[1:]] or [252]
 n = 1 << 20
 eng = pkg.Engine(0)
-opt = pkg.option(N_STEPS=steps, N_PATHS=n, B=120.0)
-buf = torch.empty(n * steps, dtype=torch.float32, device="cuda")
-cnt = torch.empty(n * steps, dtype=torch.int32, device="cuda") if want_counts else None
 st = torch.cuda.Stream()
-with torch.cuda.stream(st):
-    f = lambda: eng.trajectories_async(opt, 0, n, 1234, buf.data_ptr(), cnt.data_ptr() if want_counts else None, st.cuda_stream)
-    for _ in range(5): f()
-    st.synchronize()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(50): f()
-    b.record(); st.synchronize()
-ms = a.elapsed_time(b) / 50
-print(f"layout={os.environ.get('MCB_TRAJ_LAYOUT','default')} steps={steps} counts={want_counts}: {ms*1e3:.1f} us  {4*n*steps/ms/1e6:.1f} GB/s  {n*steps/ms/1e9:.3f} Tsteps/s  chk={float(buf[-1]):.4f}")
+
+
+def run(opt, buf, cnt, reps=50):
+    with torch.cuda.stream(st):
+        f = lambda: eng.trajectories_async(opt, 0, n, 1234, buf.data_ptr(), cnt.data_ptr() if cnt is not None else None,
+                                           st.cuda_stream)
+        for _ in range(5):
+            f()
+        st.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            f()
+        b.record()
+        st.synchronize()
+    return a.elapsed_time(b) / reps
+
+
+for steps in steps_list:
+    opt = pkg.option(N_STEPS=steps, N_PATHS=n, B=120.0)
+    for want_counts in (False, True):
+        ref = None
+        for mode, warps in ((0, 4), (1, 4), (1, 8), (1, 2)):
+            os.environ["MCB_TRAJ_MODE"] = str(mode)
+            os.environ["MCB_TRAJ_WARPS"] = str(warps)
+            buf = torch.full((n * steps,), float("nan"), dtype=torch.float32, device="cuda")
+            cnt = torch.full((n * steps,), -1, dtype=torch.int32, device="cuda") if want_counts else None
+            ms = run(opt, buf, cnt)
+            per = 8 if want_counts else 4
+            same = ""
+            if ref is None:
+                ref = (buf.clone(), cnt.clone() if cnt is not None else None)
+            else:
+                ok = bool((buf.view(torch.int32) == ref[0].view(torch.int32)).all())
+                if cnt is not None:
+                    ok = ok and bool((cnt == ref[1]).all())
+                same = "bits==mode0" if ok else "BITS DIFFER"
+            print(f"steps={steps} counts={int(want_counts)} mode={mode} warps={warps}: {ms*1e3:7.1f} us  "
+                  f"{per*n*steps/ms/1e6:7.1f} GB/s  {same}", flush=True)
+            del buf, cnt
+os.environ.pop("MCB_TRAJ_MODE", None)
+os.environ.pop("MCB_TRAJ_WARPS", None)
