@@ -66,18 +66,22 @@ int main(int argc, char **argv)
     rc |= mcb_nested_monte_carlo(engine, &nm, 0, 10, 1234, 1235, MCB_DISCOUNT_CORRECT, F, NULL, NULL, MCB_HOST, &mean_F);
     printf("C_MORE %d %.17g %.17g %.17g %.9g %.9g %.17g\n", rc, sweep[0].sum, sweep[1].sum, sweep[2].sum, (double)F[0],
            (double)F[119], mean_F);
-    /* latency of the synchronous call at the reference's own job size (hello.cu:13: 1e5 paths) */
+    /* latency of the synchronous call, from the reference's own job size (hello.cu:13: 1e5 paths) down to
+     * one path (pure call overhead: launch + ticket + final tree + host-visible result) */
     {
-        struct timespec t0, t1;
-        mcb_result r;
-        const int reps = 2000;
-        for (int i = 0; i < 50; ++i) rc |= mcb_price_european(engine, &opt, 100000, 1234, MCB_CALL, &r);
-        clock_gettime(CLOCK_MONOTONIC, &t0);
-        for (int i = 0; i < reps; ++i) rc |= mcb_price_european(engine, &opt, 100000, 1234, MCB_CALL, &r);
-        clock_gettime(CLOCK_MONOTONIC, &t1);
-        const double us = ((double)(t1.tv_sec - t0.tv_sec) * 1e9 + (double)(t1.tv_nsec - t0.tv_nsec)) / 1e3 / reps;
-        printf("C_LAT %d shards, mcb_price_european(1e5 paths): %.2f us per synchronous call\n",
-               mcb_engine_shard_count(engine), us);
+        const uint64_t sizes[4] = {1, 16384, 100000, 1000000};
+        for (int k = 0; k < 4; ++k) {
+            struct timespec t0, t1;
+            mcb_result r;
+            const int reps = 2000;
+            for (int i = 0; i < 50; ++i) rc |= mcb_price_european(engine, &opt, sizes[k], 1234, MCB_CALL, &r);
+            clock_gettime(CLOCK_MONOTONIC, &t0);
+            for (int i = 0; i < reps; ++i) rc |= mcb_price_european(engine, &opt, sizes[k], 1234, MCB_CALL, &r);
+            clock_gettime(CLOCK_MONOTONIC, &t1);
+            const double us = ((double)(t1.tv_sec - t0.tv_sec) * 1e9 + (double)(t1.tv_nsec - t0.tv_nsec)) / 1e3 / reps;
+            printf("C_LAT %d shards, mcb_price_european(%llu paths): %.2f us per synchronous call\n",
+                   mcb_engine_shard_count(engine), (unsigned long long)sizes[k], us);
+        }
     }
     free(rows);
     mcb_engine_destroy(engine);
