@@ -13,6 +13,9 @@
 #include <cstring>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <new>
 #include <string>
 #include <thread>
@@ -86,12 +89,82 @@ struct DeviceBuffer {
 
 constexpr int kHostRing = 8;   // MCB_RESULT_RING: results kept for mcb_european_collect
 
+// One launcher thread per non-leading shard of a multi-device engine: a European job is then enqueued
+// on every GPU at the same time instead of one device after the other (8 devices x ~7 us of launch
+// calls would start the last GPU ~50 us after the first -- 15 % of a 0.3 ms job).  A worker spins
+// for a little while after each job (back-to-back submits find it hot) and then sleeps.
+struct ShardWorker {
+    std::thread thread;
+    std::mutex mutex;
+    std::condition_variable wake;
+    std::atomic<unsigned long long> posted{0}, done{0};
+    std::function<int()> job;
+    int rc = 0;
+    std::string message;
+    bool quit = false;
+
+    void loop()
+    {
+        unsigned long long seen = 0;
+        for (;;) {
+            int spins = 0;
+            while (posted.load(std::memory_order_acquire) == seen) {
+                if (++spins < 200000) {
+#if defined(__x86_64__)
+                    __builtin_ia32_pause();
+#endif
+                    continue;
+                }
+                std::unique_lock<std::mutex> lock(mutex);
+                wake.wait(lock, [&] { return quit || posted.load(std::memory_order_acquire) != seen; });
+                if (quit) return;
+            }
+            if (quit) return;
+            seen = posted.load(std::memory_order_acquire);
+            rc = job();
+            done.store(seen, std::memory_order_release);
+        }
+    }
+    void post(std::function<int()> fn)
+    {
+        job = std::move(fn);
+        {
+            std::lock_guard<std::mutex> lock(mutex);   // pairs with the predicate check of a sleeping worker
+            posted.fetch_add(1, std::memory_order_release);
+        }
+        wake.notify_one();
+    }
+    int wait()
+    {
+        const unsigned long long want = posted.load(std::memory_order_acquire);
+        while (done.load(std::memory_order_acquire) != want) {
+#if defined(__x86_64__)
+            __builtin_ia32_pause();
+#endif
+        }
+        return rc;
+    }
+    void stop()
+    {
+        {
+            std::lock_guard<std::mutex> lock(mutex);
+            quit = true;
+            posted.fetch_add(1, std::memory_order_release);
+        }
+        wake.notify_one();
+        if (thread.joinable()) thread.join();
+    }
+};
+
 struct mcb_engine {
     int device = 0;
     cudaStream_t stream = nullptr;         // main stream: every pricing / trajectory launch
-    cudaStream_t f_stream = nullptr;       // final passes of world > 1 jobs (never blocks `stream`)
+    cudaStream_t stream2 = nullptr;        // odd European jobs of a world > 1 group: job e + 1 fills the SMs that
+                                           // job e's tail, segment launch and events leave idle
+    cudaStream_t f_stream = nullptr;       // final passes of world > 1 jobs (never blocks the pricing streams)
     cudaDeviceProp prop{};
     DeviceBuffer<float2> partials;
+    DeviceBuffer<float2> partials2;        // chunk partials of the jobs on stream2
     DeviceBuffer<double> segments;
     DeviceBuffer<ResultDev> results;
     DeviceBuffer<unsigned char> scratch;   // hooks / host<->device staging
@@ -102,12 +175,16 @@ struct mcb_engine {
     // ---- the job pipeline (mcb_european_submit / collect) ----
     PeerMailbox *mailbox = nullptr;        // this shard's mailbox (its own HBM)
     PeerTable peers{};                     // box[r] = shard r's mailbox as addressable from this device
-    unsigned int *seg_tickets = nullptr;   // [kSegments + 1], zero between launches
+    unsigned int *seg_tickets = nullptr;   // 2 x [kSegments + 1] (one set per pricing stream), zero between launches
+    unsigned long long last_job_epoch = 0; // mcb_last_segments: the last collected European job ...
+    uint64_t last_job_chunks = 0;          // ... and its chunk count (0: the last whole job left h_segments instead)
+    uint64_t ring_chunks[kHostRing] = {};  // chunk count of the job in each host slot
     int rank = 0, world = 1;               // this shard's place in its group
     bool in_process = false;               // group = the shards of ONE multi-device engine (events, no device spins)
     bool ipc = false;                      // group = one engine per process, mailboxes mapped over CUDA IPC
     void *peer_mapped[kMaxPeers] = {};     // what cudaIpcOpenMemHandle returned (to close on destroy)
     std::vector<mcb_engine *> shards;      // leader of a multi-device engine: every shard, itself first
+    ShardWorker *worker = nullptr;         // non-leading shard of a multi-device engine: its launcher thread
     mcb_engine *leader = nullptr;          // sub-engine of a multi-device engine: its leader
     unsigned long long job_epoch = 0;      // jobs submitted so far (leader / single engine)
     unsigned long long timeout_ns = 10ull * 1000000000ull;   // bound of every device-side wait
@@ -360,6 +437,7 @@ void launch_trajectory(const PathParams &prm_in, uint64_t n_paths, bool vec, boo
     constexpr int kSlabWarps = 4;
     PathParams prm = prm_in;
     SlabTensorMaps maps{};
+    uint64_t grid_cap = 0;
     // rows longer than one pass: one row group per slab, the whole rows staged -- while the staging
     // leaves enough CTAs per SM (measured on 2^20 rows: prices only 4.07 TB/s at 1024 steps / 32 KB,
     // 3.67 at 1536 / 48 KB, then the general kernel's 3.5 TB/s wins; with counts the general
@@ -371,9 +449,11 @@ void launch_trajectory(const PathParams &prm_in, uint64_t n_paths, bool vec, boo
     do {                                                                                                      \
         auto kern = trajectory_slab_kernel<SPL, LPR, ROWS, WARPS, CNT, LOG, MULTI, ALIGNED, FAST>;            \
         const uint64_t rows_per_cta = (uint64_t)(WARPS) * (ROWS);                                             \
-        const uint64_t ctas = (prm.n_paths + rows_per_cta - 1) / rows_per_cta;                                \
-        const size_t per_array = (FAST) ? ((((size_t)(ROWS) * (size_t)prm.n_steps + 127) & ~(size_t)127))     \
-                                        : (size_t)(ROWS) * (size_t)prm.n_steps;                               \
+        uint64_t ctas = (prm.n_paths + rows_per_cta - 1) / rows_per_cta;                                      \
+        if (grid_cap && ctas > grid_cap) ctas = grid_cap;   /* persistent: warps stride over the slabs */     \
+        const size_t per_array = ((FAST) & kFastSwizzle)                                                      \
+                                     ? ((((size_t)(ROWS) * (size_t)prm.n_steps + 127) & ~(size_t)127))        \
+                                     : (size_t)(ROWS) * (size_t)prm.n_steps;                                  \
         const size_t smem = (size_t)(WARPS) * (1 + (CNT ? 1 : 0) + (LOG ? 1 : 0)) * per_array * sizeof(float); \
         if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
         kern<<<(unsigned)ctas, (WARPS) * 32, smem, st>>>(prm, d_prices, d_counts, d_logs, maps);              \
@@ -388,39 +468,54 @@ void launch_trajectory(const PathParams &prm_in, uint64_t n_paths, bool vec, boo
             else MCB_SLAB(kRowsPerWarp, false, false, true, true);
         }
     } else if (vec && prm.n_steps <= SPL * LPR) {
-        // The fast variant (hoisted Philox products, packed FP32x2, swizzled staging + one TMA tensor
-        // store per array) takes every whole slab of 4 rows (4 * n_steps floats are whole 64-byte lines
-        // because n_steps % 4 == 0); a ragged tail of up to 3 rows goes to the linear slab kernel below.
+        // The fast variants (bit mask: 1 hoisted Philox products, 2 packed FP32x2, 4 swizzled staging + one TMA
+        // tensor store per array) take every whole slab of 4 rows (4 * n_steps floats are whole 64-byte
+        // lines because n_steps % 4 == 0); a ragged tail of up to 3 rows goes to the linear slab kernel below.
         constexpr int kFastRows = 4;
         static_assert(kFastRows % kRowsPerWarp == 0, "a slab is a whole number of passes");
         const uint64_t fast_paths = n_paths / kFastRows * kFastRows;
         const uint64_t total = fast_paths * (uint64_t)prm.n_steps;
-        const int mode = env_int("MCB_TRAJ_MODE", 1);   // 0: linear slab kernel only (round-1 path)
+        // shipped choice: arrays beyond the prices (barrier counts, log2 prices) -> all three; prices only ->
+        // the linear kernel (measured, profiles/r2_trajectory_tuning.txt).  MCB_TRAJ_MODE overrides (tools/).
+        const int mode = env_int("MCB_TRAJ_MODE", n_arrays > 1 ? kFastAll : 0);
         bool fast = mode != 0 && fast_paths > 0 && total / 16 < 0x7fffffffull;
-        if (fast) fast = encode_slab_map(&maps.prices, d_prices, total, kFastRows * (uint32_t)prm.n_steps, false);
-        if (fast && d_counts) fast = encode_slab_map(&maps.counts, d_counts, total, kFastRows * (uint32_t)prm.n_steps, true);
-        if (fast && d_logs) fast = encode_slab_map(&maps.logs, d_logs, total, kFastRows * (uint32_t)prm.n_steps, false);
+        if (fast && (mode & kFastSwizzle)) {
+            fast = encode_slab_map(&maps.prices, d_prices, total, kFastRows * (uint32_t)prm.n_steps, false);
+            if (fast && d_counts) fast = encode_slab_map(&maps.counts, d_counts, total, kFastRows * (uint32_t)prm.n_steps, true);
+            if (fast && d_logs) fast = encode_slab_map(&maps.logs, d_logs, total, kFastRows * (uint32_t)prm.n_steps, false);
+        }
         if (fast) {
             prm.n_paths = fast_paths;
-            const int warps = env_int("MCB_TRAJ_WARPS", 4);
-#define MCB_FAST(WARPS)                                                                                        \
+            grid_cap = (uint64_t)env_int("MCB_TRAJ_CTAS_PER_SM", 0) * 148ull;
+#define MCB_FAST(F)                                                                                            \
             do {                                                                                               \
-                if (d_counts && d_logs) MCB_SLAB_W(kFastRows, true, true, false, true, true, WARPS);           \
-                else if (d_counts) MCB_SLAB_W(kFastRows, true, false, false, true, true, WARPS);               \
-                else if (d_logs) MCB_SLAB_W(kFastRows, false, true, false, true, true, WARPS);                 \
-                else MCB_SLAB_W(kFastRows, false, false, false, true, true, WARPS);                            \
+                if (d_counts && d_logs) MCB_SLAB_W(kFastRows, true, true, false, true, F, kSlabWarps);         \
+                else if (d_counts) MCB_SLAB_W(kFastRows, true, false, false, true, F, kSlabWarps);             \
+                else if (d_logs) MCB_SLAB_W(kFastRows, false, true, false, true, F, kSlabWarps);               \
+                else MCB_SLAB_W(kFastRows, false, false, false, true, F, kSlabWarps);                          \
             } while (0)
-            if (warps == 8) MCB_FAST(8);
-            else if (warps == 2) MCB_FAST(2);
-            else MCB_FAST(4);
+            bool launched = true;
+            if (mode == kFastAll) MCB_FAST(kFastAll);
+            else if constexpr (SPL * LPR == 256) {   // the partial combinations exist for the tuning sweep only
+                if (mode == 1) MCB_FAST(1);
+                else if (mode == 4) MCB_FAST(4);
+                else if (mode == 5) MCB_FAST(5);
+                else if (mode == 3) MCB_FAST(3);
+                else launched = false;
+            } else launched = false;
 #undef MCB_FAST
-            // the tail: rows [fast_paths, n_paths) through the linear kernel
-            prm.first_path = prm_in.first_path + fast_paths;
-            prm.n_paths = n_paths - fast_paths;
-            const uint64_t off = fast_paths * (uint64_t)prm.n_steps;
-            d_prices += off;
-            if (d_counts) d_counts += off;
-            if (d_logs) d_logs += off;
+            grid_cap = 0;
+            if (launched) {
+                // the tail: rows [fast_paths, n_paths) through the linear kernel
+                prm.first_path = prm_in.first_path + fast_paths;
+                prm.n_paths = n_paths - fast_paths;
+                const uint64_t off = fast_paths * (uint64_t)prm.n_steps;
+                d_prices += off;
+                if (d_counts) d_counts += off;
+                if (d_logs) d_logs += off;
+            } else {
+                prm.n_paths = n_paths;
+            }
         }
         // rows per slab: ~6 for one output array (tuned on B200 at 2^20 x 252, profiles/r1_trajectory_tuning.txt),
         // fewer when counts / logs need their own staging rows; always a whole number of passes
@@ -488,6 +583,7 @@ static int engine_create_one(int device, mcb_engine **out)
     int prio_lo = 0, prio_hi = 0;
     if (err == cudaSuccess) err = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
+    if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking);
     // the final passes are single warps that must not queue behind thousands of pricing CTAs
     if (err == cudaSuccess) err = cudaStreamCreateWithPriority(&e->f_stream, cudaStreamNonBlocking, prio_hi);
     if (err == cudaSuccess)
@@ -497,8 +593,8 @@ static int engine_create_one(int device, mcb_engine **out)
         err = cudaHostAlloc(&e->h_ring, sizeof(HostSlot) * kHostRing, cudaHostAllocMapped | cudaHostAllocPortable);
     if (err == cudaSuccess) err = cudaMalloc(&e->mailbox, sizeof(PeerMailbox));
     if (err == cudaSuccess) err = cudaMemset(e->mailbox, 0, sizeof(PeerMailbox));
-    if (err == cudaSuccess) err = cudaMalloc(&e->seg_tickets, sizeof(unsigned int) * (kSegments + 1));
-    if (err == cudaSuccess) err = cudaMemset(e->seg_tickets, 0, sizeof(unsigned int) * (kSegments + 1));
+    if (err == cudaSuccess) err = cudaMalloc(&e->seg_tickets, sizeof(unsigned int) * 2 * (kSegments + 1));
+    if (err == cudaSuccess) err = cudaMemset(e->seg_tickets, 0, sizeof(unsigned int) * 2 * (kSegments + 1));
     for (int i = 0; i < kRing && err == cudaSuccess; ++i) {
         err = cudaEventCreateWithFlags(&e->p_done[i], cudaEventDisableTiming);
         if (err == cudaSuccess) err = cudaEventCreateWithFlags(&e->f_done[i], cudaEventDisableTiming);
@@ -572,6 +668,10 @@ int mcb_engine_create_multi(const int *devices, int n_devices, mcb_engine **out)
             s->in_process = true;
             s->leader = i ? L : nullptr;
             for (size_t r = 0; r < shards.size(); ++r) s->peers.box[r] = shards[r]->mailbox;
+            if (i) {
+                s->worker = new (std::nothrow) ShardWorker();
+                if (s->worker) s->worker->thread = std::thread([w = s->worker] { w->loop(); });
+            }
         }
         L->shards = shards;
     }
@@ -592,12 +692,19 @@ int mcb_engine_destroy(mcb_engine *e)
             mcb_engine_destroy(s);
         }
     }
+    if (e->worker) {
+        e->worker->stop();
+        delete e->worker;
+        e->worker = nullptr;
+    }
     DeviceGuard g(e->device);
     if (e->stream) {
         cudaStreamSynchronize(e->stream);
+        if (e->stream2) cudaStreamSynchronize(e->stream2);
         if (e->f_stream) cudaStreamSynchronize(e->f_stream);
         cudaStreamDestroy(e->stream);
     }
+    if (e->stream2) cudaStreamDestroy(e->stream2);
     if (e->f_stream) cudaStreamDestroy(e->f_stream);
     for (auto *v : {&e->timed, &e->event_pool})
         for (auto &t : *v) {
@@ -611,6 +718,7 @@ int mcb_engine_destroy(mcb_engine *e)
     if (e->t_begin) cudaEventDestroy(e->t_begin);
     if (e->t_end) cudaEventDestroy(e->t_end);
     e->partials.release();
+    e->partials2.release();
     e->segments.release();
     e->results.release();
     e->scratch.release();
@@ -651,6 +759,7 @@ static int sync_all(mcb_engine *e)
         mcb_engine *s = e->shards.empty() ? e : e->shards[i];
         DeviceGuard g(s->device);
         CU(cudaStreamSynchronize(s->stream));
+        CU(cudaStreamSynchronize(s->stream2));
         CU(cudaStreamSynchronize(s->f_stream));
     }
     return MCB_OK;
@@ -696,6 +805,7 @@ int mcb_peer_mailbox_connect(mcb_engine *e, int rank, int world, const void *all
                     (unsigned long long)base_epoch, e->job_epoch);
     DeviceGuard g(e->device);
     CU(cudaStreamSynchronize(e->stream));
+    CU(cudaStreamSynchronize(e->stream2));
     CU(cudaStreamSynchronize(e->f_stream));
     const cudaIpcMemHandle_t *h = static_cast<const cudaIpcMemHandle_t *>(all_handles);
     for (int r = 0; r < kMaxPeers; ++r) {
@@ -764,21 +874,29 @@ int submit_shard(mcb_engine *s, mcb_engine *L, const mcb_option_data *opt, uint6
     if (!g.ok) return fail(MCB_ERR_CUDA, "cudaSetDevice(%d) failed", s->device);
     const int rank = s->rank, world = s->world;
     const int slot = (int)(epoch % kRing);
+    // groups of several shards alternate their jobs between two pricing streams: the next job's CTAs
+    // take the SM slots this job's last wave, segment launch and event records leave idle
+    const int lane = (world > 1) ? (int)(epoch & 1ull) : 0;
+    cudaStream_t st = lane ? s->stream2 : s->stream;
+    DeviceBuffer<float2> &partials = lane ? s->partials2 : s->partials;
     const uint64_t n_chunks = (n_paths + kEuropeanChunk - 1) / kEuropeanChunk;
     int seg_lo, seg_hi;
     uint64_t c_lo, c_hi;
     segment_span(rank, world, n_chunks, &seg_lo, &seg_hi, &c_lo, &c_hi);
     if (c_hi - c_lo > 0x7fffffffull) return fail(MCB_ERR_INVALID, "too many chunks for one launch");
     int rc;
-    if ((rc = s->partials.reserve((size_t)(c_hi - c_lo) + 1))) return rc;
+    if (partials.cap < (size_t)(c_hi - c_lo) + 1) {
+        CU(cudaStreamSynchronize(st));   // growing the workspace frees the old one: nothing may still use it
+        if ((rc = partials.reserve((size_t)(c_hi - c_lo) + 1))) return rc;
+    }
     // in-process groups pace themselves with events: the mailbox slot of job epoch - kRing must have
     // been folded by the leader before this job's stores land in it (separate processes use acks)
-    if (s->in_process && epoch > (unsigned long long)kRing) CU(cudaStreamWaitEvent(s->stream, L->f_done[slot], 0));
+    if (s->in_process && epoch > (unsigned long long)kRing) CU(cudaStreamWaitEvent(st, L->f_done[slot], 0));
     JobArgs args{};
     args.n_chunks = n_chunks;
     args.n_paths = n_paths;
     args.discount = std::exp(-(double)opt->r * (double)opt->T);
-    args.seg_tickets = s->seg_tickets;
+    args.seg_tickets = s->seg_tickets + lane * (kSegments + 1);
     args.peers = s->peers;
     args.epoch = epoch;
     args.timeout_ns = s->timeout_ns;
@@ -795,30 +913,29 @@ int submit_shard(mcb_engine *s, mcb_engine *L, const mcb_option_data *opt, uint6
     if (world == 1) {
         args.d_out = s->results.ptr;
         args.h_out = &s->h_ring[epoch % kHostRing];
-        args.h_segments = s->h_segments;
     }
     if (c_hi - c_lo >= kTwoLaunchChunks) {
         // large shard: the plain pricing kernel, then one CTA per owned segment (see segments_job_kernel)
         const EuropeanParams prm = european_params(opt, opt->K, opt->v, n_paths, seed, c_lo);
-        if ((rc = launch_european<MCB_EUROPEAN_PATHS_PER_SLOT>(s, prm, option_type, c_hi - c_lo, s->partials.ptr,
-                                                               nullptr, 0, s->stream)))
+        if ((rc = launch_european<MCB_EUROPEAN_PATHS_PER_SLOT>(s, prm, option_type, c_hi - c_lo, partials.ptr, nullptr, 0,
+                                                               st)))
             return rc;
-        segments_job_kernel<<<(unsigned)(seg_hi - seg_lo), kSlots, 0, s->stream>>>(args, s->partials.ptr, c_lo);
+        segments_job_kernel<<<(unsigned)(seg_hi - seg_lo), kSlots, 0, st>>>(args, partials.ptr, c_lo);
     } else if (c_hi > c_lo) {
         const EuropeanParams prm = european_params(opt, opt->K, opt->v, n_paths, seed, c_lo);
-        TimedScope timed(s, MCB_KERNEL_EUROPEAN, s->stream);
+        TimedScope timed(s, MCB_KERNEL_EUROPEAN, st);
         if (option_type == MCB_PUT)
-            european_job_kernel<kPut, MCB_EUROPEAN_PATHS_PER_SLOT><<<(unsigned)(c_hi - c_lo), kSlots, 0, s->stream>>>(
-                prm, args, s->partials.ptr);
+            european_job_kernel<kPut, MCB_EUROPEAN_PATHS_PER_SLOT><<<(unsigned)(c_hi - c_lo), kSlots, 0, st>>>(
+                prm, args, partials.ptr);
         else
-            european_job_kernel<kCall, MCB_EUROPEAN_PATHS_PER_SLOT><<<(unsigned)(c_hi - c_lo), kSlots, 0, s->stream>>>(
-                prm, args, s->partials.ptr);
+            european_job_kernel<kCall, MCB_EUROPEAN_PATHS_PER_SLOT><<<(unsigned)(c_hi - c_lo), kSlots, 0, st>>>(
+                prm, args, partials.ptr);
     } else {
-        job_publish_empty_kernel<<<1, kSegments, 0, s->stream>>>(args);
+        job_publish_empty_kernel<<<1, 32, 0, st>>>(args);
     }
-    L->launches++;
+    s->launches++;
     CU(cudaGetLastError());
-    if (world > 1) CU(cudaEventRecord(s->p_done[slot], s->stream));
+    if (world > 1) CU(cudaEventRecord(s->p_done[slot], st));
     return MCB_OK;
 }
 
@@ -843,17 +960,35 @@ int mcb_european_submit(mcb_engine *e, const mcb_option_data *opt, uint64_t n_pa
     HostSlot *hs = &e->h_ring[epoch % kHostRing];
     hs->seq = 0;                      // the job that used this slot kHostRing tickets ago expires here
     e->h_ring_paths[epoch % kHostRing] = n_paths;
+    e->ring_chunks[epoch % kHostRing] = (n_paths + kEuropeanChunk - 1) / kEuropeanChunk;
     std::atomic_thread_fence(std::memory_order_seq_cst);
     const size_t n = shard_count(e);
-    for (size_t i = 0; i < n; ++i)
-        if ((rc = submit_shard(shard_at(e, i), e, opt, n_paths, seed, option_type, epoch))) return rc;
+    // the other shards' launcher threads enqueue their devices while this thread does the leader's
+    for (size_t i = 1; i < n; ++i) {
+        mcb_engine *s = shard_at(e, i);
+        if (!s->worker) continue;
+        s->worker->post([=]() {
+            const int r = submit_shard(s, e, opt, n_paths, seed, option_type, epoch);
+            if (r != MCB_OK) s->worker->message = g_error;
+            return r;
+        });
+    }
+    rc = submit_shard(e, e, opt, n_paths, seed, option_type, epoch);
+    for (size_t i = 1; i < n; ++i) {
+        mcb_engine *s = shard_at(e, i);
+        const int r = s->worker ? s->worker->wait() : submit_shard(s, e, opt, n_paths, seed, option_type, epoch);
+        if (r != MCB_OK && rc == MCB_OK) {
+            rc = s->worker ? fail(r, "shard %zu (device %d): %s", i, s->device, s->worker->message.c_str()) : r;
+        }
+    }
+    if (rc) return rc;
     if (e->world > 1) {
         DeviceGuard g(e->device);
         const int slot = (int)(epoch % kRing);
         for (size_t i = 0; i < n; ++i) CU(cudaStreamWaitEvent(e->f_stream, shard_at(e, i)->p_done[slot], 0));
         combine_job_kernel<<<1, 32, 0, e->f_stream>>>(e->peers, e->rank, e->world, e->ipc ? 1 : 0, epoch, e->timeout_ns,
-                                                      n_paths, std::exp(-(double)opt->r * (double)opt->T),
-                                                      e->results.ptr, hs, e->h_segments);
+                                                      (n_paths + kEuropeanChunk - 1) / kEuropeanChunk, n_paths,
+                                                      std::exp(-(double)opt->r * (double)opt->T), e->results.ptr, hs);
         e->launches++;
         CU(cudaGetLastError());
         CU(cudaEventRecord(e->f_done[slot], e->f_stream));
@@ -877,6 +1012,8 @@ int mcb_european_collect(mcb_engine *e, uint64_t ticket, mcb_result *out)
         if ((++spins & 0x3fff) == 0) {
             DeviceGuard g(e->device);
             cudaError_t qa = cudaStreamQuery(e->stream), qb = cudaStreamQuery(e->f_stream);
+            const cudaError_t qc = cudaStreamQuery(e->stream2);
+            if (qa == cudaSuccess) qa = qc;
             if ((qa != cudaSuccess && qa != cudaErrorNotReady) || (qb != cudaSuccess && qb != cudaErrorNotReady))
                 return fail(MCB_ERR_CUDA, "stream failed while waiting for ticket %llu: %s", (unsigned long long)ticket,
                             cudaGetErrorString(qa != cudaSuccess && qa != cudaErrorNotReady ? qa : qb));
@@ -884,7 +1021,8 @@ int mcb_european_collect(mcb_engine *e, uint64_t ticket, mcb_result *out)
                 bool idle = true;       // multi-device: every shard's stream must have drained too
                 for (size_t i = 1; i < shard_count(e) && idle; ++i) {
                     DeviceGuard gs(shard_at(e, i)->device);
-                    idle = cudaStreamQuery(shard_at(e, i)->stream) == cudaSuccess;
+                    idle = cudaStreamQuery(shard_at(e, i)->stream) == cudaSuccess &&
+                           cudaStreamQuery(shard_at(e, i)->stream2) == cudaSuccess;
                 }
                 if (idle && hs->seq != ticket) {
                     std::atomic_thread_fence(std::memory_order_seq_cst);
@@ -902,6 +1040,8 @@ int mcb_european_collect(mcb_engine *e, uint64_t ticket, mcb_result *out)
     }
     std::atomic_thread_fence(std::memory_order_acquire);
     memcpy(out, const_cast<const ResultDev *>(&hs->result), sizeof(mcb_result));
+    e->last_job_epoch = ticket;
+    e->last_job_chunks = e->ring_chunks[ticket % kHostRing];
     if (out->n_paths == 0 || out->price != out->price)
         return fail(MCB_ERR_TIMEOUT, "ticket %llu: a peer did not deliver its segments within %.1f s (result poisoned)",
                     (unsigned long long)ticket, (double)e->timeout_ns * 1e-9);
@@ -917,9 +1057,10 @@ int mcb_pipeline_timer_start(mcb_engine *e)
     CU(cudaEventRecord(e->t_begin, e->stream));
     // nothing of the timed jobs may start before t_begin, on any stream of any shard
     CU(cudaStreamWaitEvent(e->f_stream, e->t_begin, 0));
-    for (size_t i = 1; i < shard_count(e); ++i) {
+    for (size_t i = 0; i < shard_count(e); ++i) {
         DeviceGuard gs(shard_at(e, i)->device);
-        CU(cudaStreamWaitEvent(shard_at(e, i)->stream, e->t_begin, 0));
+        if (i) CU(cudaStreamWaitEvent(shard_at(e, i)->stream, e->t_begin, 0));
+        CU(cudaStreamWaitEvent(shard_at(e, i)->stream2, e->t_begin, 0));
     }
     return MCB_OK;
 }
@@ -933,11 +1074,13 @@ int mcb_pipeline_timer_stop(mcb_engine *e, double *elapsed_ms)
         for (size_t i = 0; i < shard_count(e); ++i) {
             mcb_engine *s = shard_at(e, i);
             DeviceGuard gs(s->device);
-            cudaEvent_t tmp = nullptr;
-            CU(cudaEventCreateWithFlags(&tmp, cudaEventDisableTiming));
-            CU(cudaEventRecord(tmp, s->stream));
-            CU(cudaStreamWaitEvent(e->f_stream, tmp, 0));
-            CU(cudaEventDestroy(tmp));   // released once the wait has consumed it
+            for (cudaStream_t st : {s->stream, s->stream2}) {
+                cudaEvent_t tmp = nullptr;
+                CU(cudaEventCreateWithFlags(&tmp, cudaEventDisableTiming));
+                CU(cudaEventRecord(tmp, st));
+                CU(cudaStreamWaitEvent(e->f_stream, tmp, 0));
+                CU(cudaEventDestroy(tmp));   // released once the wait has consumed it
+            }
         }
         CU(cudaEventRecord(e->t_end, e->f_stream));
         CU(cudaEventSynchronize(e->t_end));
@@ -1031,6 +1174,7 @@ int mcb_combine_segments_async(mcb_engine *e, const double *d_segments, int n_se
 static int finish_whole_job(mcb_engine *e, int n_sets, uint64_t n_paths, float r, float T, mcb_result *out)
 {
     int rc;
+    e->last_job_chunks = 0;   // mcb_last_segments: this job leaves its segments in h_segments
     if (n_sets == 1) {
         // single job (the reference's wrapper-sized calls): the result lands right behind the 64
         // segments, so ONE small D2H copy brings both back (a 1e6-path call is ~40 us end to end,
@@ -1803,7 +1947,19 @@ int mcb_bullet_payoffs(mcb_engine *e, const mcb_option_data *opt, uint64_t first
 int mcb_last_segments(mcb_engine *e, double *segments)
 {
     if (!e || !segments) return fail(MCB_ERR_INVALID, "NULL argument");
-    memcpy(segments, e->h_segments, sizeof(double) * 2 * MCB_SEGMENTS);
+    if (e->last_job_chunks == 0) {   // bullet / sweep: copied home with the result
+        memcpy(segments, e->h_segments, sizeof(double) * 2 * MCB_SEGMENTS);
+        return MCB_OK;
+    }
+    // European job: its segments are still in the mailbox slot of its epoch (until kRing jobs later)
+    if (e->job_epoch - e->last_job_epoch >= (unsigned long long)kRing)
+        return fail(MCB_ERR_INVALID, "the segments of the last collected job have been overwritten");
+    DeviceGuard g(e->device);
+    CU(cudaMemcpy(segments, e->mailbox->gather[e->last_job_epoch % kRing], sizeof(double) * 2 * MCB_SEGMENTS,
+                  cudaMemcpyDeviceToHost));
+    for (int sg = 0; sg < MCB_SEGMENTS; ++sg)   // segments without a chunk are +0.0 by rule (never stored)
+        if ((e->last_job_chunks * (uint64_t)sg) / MCB_SEGMENTS == (e->last_job_chunks * (uint64_t)(sg + 1)) / MCB_SEGMENTS)
+            segments[2 * sg] = segments[2 * sg + 1] = 0.0;
     return MCB_OK;
 }
 

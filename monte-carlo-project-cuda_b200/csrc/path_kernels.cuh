@@ -339,8 +339,10 @@ __device__ __forceinline__ void tensor_store_2d(void *smem, const CUtensorMap *m
                  :: "l"(map), "r"(smem_addr(smem)), "r"(c0), "r"(c1) : "memory");
 }
 
+enum { kFastHoist = 1, kFastPack = 2, kFastSwizzle = 4, kFastAll = 7 };
+
 template <int SPL, int LPR, int ROWS, int WARPS, bool COUNTS, bool LOGS, bool MULTI = false, bool ALIGNED = true,
-          bool FAST = false>
+          int FAST = 0>
 __global__ void __launch_bounds__(WARPS * 32)
 trajectory_slab_kernel(const __grid_constant__ PathParams prm, float *__restrict__ prices, int *__restrict__ counts,
                        float *__restrict__ logs, const __grid_constant__ SlabTensorMaps maps)
@@ -360,11 +362,11 @@ trajectory_slab_kernel(const __grid_constant__ PathParams prm, float *__restrict
     const uint32_t slab_stride = gridDim.x * WARPS;   // a warp strides over the slabs (one each when the grid covers them)
     const int lane_step = SPL * ln;
     // floats between the arrays of a slab in shared memory: dense, or rounded up to the swizzle period
-    const int slab_floats = FAST ? ((ROWS * n_steps + 127) & ~127) : ROWS * n_steps;
+    const int slab_floats = (FAST & kFastSwizzle) ? ((ROWS * n_steps + 127) & ~127) : ROWS * n_steps;
     float *my_stage = stage + (size_t)warp * kArrays * slab_floats;
     float *dst0 = my_stage + sub * n_steps + lane_step;
     RowHoist<SPL> hoist;
-    if (FAST) hoist = make_row_hoist<SPL>(prm, (uint32_t)(prm.first_path >> 32), lane_step);
+    if (FAST & kFastHoist) hoist = make_row_hoist<SPL>(prm, (uint32_t)(prm.first_path >> 32), lane_step);
 
 #pragma unroll 1
     for (uint32_t slab = blockIdx.x * WARPS + warp; slab < n_slabs; slab += slab_stride) {
@@ -383,11 +385,12 @@ trajectory_slab_kernel(const __grid_constant__ PathParams prm, float *__restrict
                 const int my_step = step0 + lane_step;
                 const bool active = my_step < n_steps;
                 PassWords<SPL> words;
-                if (FAST && (uint32_t)(p >> 32) == hoist.p_hi) words = row_words_hoisted<SPL>(prm, hoist, (uint32_t)p);
+                if ((FAST & kFastHoist) && (uint32_t)(p >> 32) == hoist.p_hi)
+                    words = row_words_hoisted<SPL>(prm, hoist, (uint32_t)p);
                 else words = row_words<SPL>(prm, (uint32_t)p, (uint32_t)(p >> 32), my_step);
                 float a[SPL];
-                const float base = row_finish<SPL, LPR, FAST>(prm, words, active, carry_l, a);
-                if (FAST) {                                                  // log2 prices of this lane's steps
+                const float base = row_finish<SPL, LPR, (FAST & kFastPack) != 0>(prm, words, active, carry_l, a);
+                if (FAST & kFastPack) {                                      // log2 prices of this lane's steps
                     const uint64_t bb = f2_pack(base, base);
 #pragma unroll
                     for (int j = 0; j < SPL; j += 2) f2_unpack(f2_add(f2_pack(a[j], a[j + 1]), bb), a[j], a[j + 1]);
@@ -422,7 +425,7 @@ trajectory_slab_kernel(const __grid_constant__ PathParams prm, float *__restrict
                                 c[j] = cbase;
                             }
                         }
-                        if (FAST) {
+                        if (FAST & kFastSwizzle) {
                             // 64-byte swizzle on the slab-linear offset: 16-byte unit index ^= (offset >> 7) & 3
                             const uint32_t lin = (uint32_t)((r + sub) * n_steps + lane_step + 4 * b) * 4u;
                             float *sw = my_stage + ((lin ^ ((lin >> 3) & 0x30u)) >> 2);
@@ -454,7 +457,7 @@ trajectory_slab_kernel(const __grid_constant__ PathParams prm, float *__restrict
         }
         fence_async_smem();   // generic-proxy STS -> visible to the async proxy (TMA)
         __syncwarp();
-        if (FAST) {
+        if (FAST & kFastSwizzle) {
             // the host launches this variant on whole slabs only; ONE tensor store per array un-swizzles
             if (lane == 0) {
                 const int line = (int)(((uint64_t)slab_row * (uint32_t)n_steps) >> 4);   // 64-byte line of the slab
@@ -525,6 +528,11 @@ nested_kernel(const __grid_constant__ NestedParams prm, const float *__restrict_
         float sum = 0.0f, sq = 0.0f;
         if (co <= prm.P2) {
             const uint64_t q = (p * (uint64_t)n_steps + (uint64_t)k) * (uint64_t)prm.n_inner;
+            // the point's inner streams q .. q + n_inner - 1 share their high word unless they straddle a
+            // multiple of 2^32 (CTA-uniform test): then the round-1 product that depends on it is computed
+            // once per warp on the uniform datapath instead of per thread on the multiplier pipe
+            const bool hi_uniform = (uint32_t)q + (uint32_t)(prm.n_inner - 1) >= (uint32_t)q;
+            const uint32_t q_hi = (uint32_t)(q >> 32);
             int jj = threadIdx.x;
 #pragma unroll 1
             for (; jj + kSlots < prm.n_inner; jj += 2 * kSlots) {   // two inner paths interleaved
@@ -532,8 +540,13 @@ nested_kernel(const __grid_constant__ NestedParams prm, const float *__restrict_
                 float l[2] = {lo, lo};
                 int c[2] = {co, co};
                 const uint32_t s_lo[2] = {(uint32_t)sa, (uint32_t)sb};
-                const uint32_t s_hi[2] = {(uint32_t)(sa >> 32), (uint32_t)(sb >> 32)};
-                walk_paths<2>(l, c, s_lo, s_hi, remaining, prm.sc, prm.dr, prm.lB, prm.keys_inner);
+                if (hi_uniform) {
+                    const uint32_t s_hi[2] = {q_hi, q_hi};
+                    walk_paths<2>(l, c, s_lo, s_hi, remaining, prm.sc, prm.dr, prm.lB, prm.keys_inner);
+                } else {
+                    const uint32_t s_hi[2] = {(uint32_t)(sa >> 32), (uint32_t)(sb >> 32)};
+                    walk_paths<2>(l, c, s_lo, s_hi, remaining, prm.sc, prm.dr, prm.lB, prm.keys_inner);
+                }
 #pragma unroll
                 for (int k = 0; k < 2; ++k) {
                     const float pay = (c[k] >= prm.P1 && c[k] <= prm.P2) ? fmaxf(mufu_ex2(l[k]) - prm.K, 0.0f) : 0.0f;

@@ -312,7 +312,11 @@ bullet_kernel(const __grid_constant__ WalkParams prm, float2 *__restrict__ parti
             const uint64_t pa = base + local, pb = pa + kSlots;
             float l[2] = {prm.l0, prm.l0};
             int count[2] = {prm.count0, prm.count0};
-            const uint32_t lo[2] = {(uint32_t)pa, (uint32_t)pb}, hi[2] = {(uint32_t)(pa >> 32), (uint32_t)(pb >> 32)};
+            // a chunk (1024 consecutive, 1024-aligned paths) never straddles a multiple of 2^32: the high
+            // stream word is the CTA-uniform high word of `base`, so the round-1 product it feeds
+            // (M1 * (hi(M0 * block) ^ p_hi ^ k1[0])) lives on the uniform datapath, off the multiplier pipe
+            const uint32_t p_hi = (uint32_t)(base >> 32);
+            const uint32_t lo[2] = {(uint32_t)pa, (uint32_t)pb}, hi[2] = {p_hi, p_hi};
             walk_paths<2>(l, count, lo, hi, prm.n_steps, prm.sc, prm.dr, prm.lB, prm.keys);
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
@@ -454,7 +458,6 @@ struct JobArgs {
     PeerTable peers;
     ResultDev *d_out;               // world == 1: device copy of the result (nullable)
     HostSlot *h_out;                // world == 1: mapped host slot (nullable)
-    double *h_segments;             // world == 1: mapped host [kSegments][2] (nullable)
     unsigned long long epoch;       // job number, > 0, agreed by every shard
     unsigned long long timeout_ns;  // bound of every device-side wait
     int seg_lo, seg_hi;             // segments this shard owns
@@ -487,13 +490,21 @@ __device__ __noinline__ bool wait_at_least(const volatile unsigned long long *p,
     return true;
 }
 
-// The fixed 64 -> 1 tree of combine_kernel, run by one warp on a mailbox slot; ok == false (a
+// The fixed 64 -> 1 tree of combine_kernel, run by one warp on a mailbox slot.  Segments without a
+// chunk (jobs of fewer than 64 chunks) are +0.0 by rule and are never stored or read; ok == false (a
 // peer never arrived) poisons the result with NaN and n_paths = 0 instead of a plausible number.
-__device__ __forceinline__ void final_tree_warp(const volatile double *seg, int lane, uint64_t n_paths, double discount,
-                                                bool ok, unsigned long long epoch, ResultDev *d_out, HostSlot *h_out)
+__device__ __forceinline__ bool segment_is_empty(uint64_t n_chunks, int seg)
 {
-    double s = seg[2 * lane] + seg[2 * (lane + 32)];
-    double q = seg[2 * lane + 1] + seg[2 * (lane + 32) + 1];
+    return (n_chunks * (uint64_t)seg) / kSegments == (n_chunks * (uint64_t)(seg + 1)) / kSegments;
+}
+
+__device__ __forceinline__ void final_tree_warp(const volatile double *seg, int lane, uint64_t n_chunks, uint64_t n_paths,
+                                                double discount, bool ok, unsigned long long epoch, ResultDev *d_out,
+                                                HostSlot *h_out)
+{
+    const bool lo_live = !segment_is_empty(n_chunks, lane), hi_live = !segment_is_empty(n_chunks, lane + 32);
+    double s = (lo_live ? seg[2 * lane] : 0.0) + (hi_live ? seg[2 * (lane + 32)] : 0.0);
+    double q = (lo_live ? seg[2 * lane + 1] : 0.0) + (hi_live ? seg[2 * (lane + 32) + 1] : 0.0);
     s = warp_fold(s);
     q = warp_fold(q);
     if (lane == 0) {
@@ -523,21 +534,11 @@ __device__ __forceinline__ void final_tree_warp(const volatile double *seg, int 
     }
 }
 
-// Fold segment `seg` of this shard (all kSlots threads, same order as segment_kernel), store it into
-// every consumer's mailbox slot, and -- in the CTA that completes the shard's last segment -- write
-// the empty segments, publish the flag and (world == 1) run the final tree.
-__device__ __forceinline__ void job_fold_and_publish(const JobArgs &args, const float2 *__restrict__ partials,
-                                                     uint64_t first_chunk, int seg, double *dscratch, int *flag)
+// Store segment `seg` = (a, b) of this shard into every consumer's mailbox slot, and -- in the CTA that
+// completes the shard's last segment -- publish the flag or (world == 1) run the final tree.
+// Called by thread 0's (a, b); every thread of the CTA takes part in the barrier.
+__device__ __forceinline__ void job_publish_segment(const JobArgs &args, int seg, double a, double b, int *flag)
 {
-    const uint64_t n = args.n_chunks;
-    const uint64_t lo = (n * (uint64_t)seg) / kSegments, hi = (n * (uint64_t)(seg + 1)) / kSegments;
-    double a = 0.0, b = 0.0;
-    for (uint64_t c = lo + threadIdx.x; c < hi; c += kSlots) {
-        const float2 v = __ldcg(partials + (c - first_chunk));
-        a = a + (double)v.x;
-        b = b + (double)v.y;
-    }
-    block_fold2(a, b, dscratch);
     const int slot = (int)(args.epoch % (unsigned long long)kRing);
     PeerMailbox *mine = args.peers.box[args.rank];
     if (threadIdx.x == 0) {
@@ -559,19 +560,6 @@ __device__ __forceinline__ void job_fold_and_publish(const JobArgs &args, const 
     if (!flag[1]) return;
     // ---- the CTA that completed this shard's last segment ------------------------------------
     __threadfence();
-    if (args.live_segments < args.seg_hi - args.seg_lo) {   // owned segments without a chunk hold +0.0
-        for (int s = args.seg_lo + (int)threadIdx.x; s < args.seg_hi; s += kSlots) {
-            if ((n * (uint64_t)s) / kSegments == (n * (uint64_t)(s + 1)) / kSegments) {
-                for (int c = 0; c < args.n_consumers; ++c) {
-                    double *dst = args.peers.box[c]->gather[slot] + 2 * s;
-                    __stcg(dst, 0.0);
-                    __stcg(dst + 1, 0.0);
-                }
-            }
-        }
-        if (args.world > 1) __threadfence_system(); else __threadfence();
-        __syncthreads();
-    }
     if (threadIdx.x == 0) args.seg_tickets[kSegments] = 0u;   // ready for the next launch
     if (args.world > 1) {
         if (threadIdx.x < (unsigned)args.n_consumers)
@@ -579,35 +567,57 @@ __device__ __forceinline__ void job_fold_and_publish(const JobArgs &args, const 
         return;
     }
     // world == 1: every segment is here; finish the job in this launch
-    const volatile double *sg = mine->gather[slot];
-    if (args.h_segments && threadIdx.x < 2 * kSegments)
-        reinterpret_cast<volatile double *>(args.h_segments)[threadIdx.x] = sg[threadIdx.x];
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        if (args.h_segments) __threadfence_system();
-        final_tree_warp(sg, (int)threadIdx.x, args.n_paths, args.discount, true, args.epoch, args.d_out, args.h_out);
-    }
+    if (threadIdx.x < 32)
+        final_tree_warp(mine->gather[slot], (int)threadIdx.x, args.n_chunks, args.n_paths, args.discount, true,
+                        args.epoch, args.d_out, args.h_out);
 }
 
-// Tail of european_job_kernel: a ticket per segment finds the last CTA of each.
+// Fold segment `seg` of this shard (all kSlots threads, same order as segment_kernel) and publish it.
+__device__ __forceinline__ void job_fold_and_publish(const JobArgs &args, const float2 *__restrict__ partials,
+                                                     uint64_t first_chunk, int seg, double *dscratch, int *flag)
+{
+    const uint64_t n = args.n_chunks;
+    const uint64_t lo = (n * (uint64_t)seg) / kSegments, hi = (n * (uint64_t)(seg + 1)) / kSegments;
+    double a = 0.0, b = 0.0;
+    for (uint64_t c = lo + threadIdx.x; c < hi; c += kSlots) {
+        const float2 v = __ldcg(partials + (c - first_chunk));
+        a = a + (double)v.x;
+        b = b + (double)v.y;
+    }
+    block_fold2(a, b, dscratch);
+    job_publish_segment(args, seg, a, b, flag);
+}
+
+// Tail of european_job_kernel: a ticket per segment finds the last CTA of each.  A segment that
+// consists of this one chunk (every job of at most 64 chunks, i.e. the reference's own call sizes)
+// needs neither ticket nor fence nor a second look at memory: its 256-slot double tree has a single
+// non-zero slot, so the segment IS (double)partial, straight from thread 0's registers.
 __device__ __noinline__ void job_tail(const JobArgs &args, const float2 *__restrict__ partials, uint64_t first_chunk,
-                                      double *dscratch, int *flag)
+                                      float2 mine, double *dscratch, int *flag)
 {
     const uint64_t chunk = first_chunk + blockIdx.x;
     const uint64_t n = args.n_chunks;
     if (threadIdx.x == 0) {
-        __threadfence();                                    // my partial is visible device-wide
         int seg = (int)((chunk * (uint64_t)kSegments) / n);
         while ((n * (uint64_t)(seg + 1)) / kSegments <= chunk) ++seg;
         while ((n * (uint64_t)seg) / kSegments > chunk) --seg;
         const uint64_t lo = (n * (uint64_t)seg) / kSegments, hi = (n * (uint64_t)(seg + 1)) / kSegments;
-        const unsigned int t = atomicAdd(&args.seg_tickets[seg], 1u);
-        flag[0] = (t == (unsigned int)(hi - lo) - 1u) ? seg : -1;
-        if (flag[0] >= 0) args.seg_tickets[seg] = 0u;       // ready for the next launch
+        if (hi - lo == 1) {
+            flag[0] = seg | 0x100;                          // alone in its segment
+        } else {
+            __threadfence();                                // my partial is visible device-wide
+            const unsigned int t = atomicAdd(&args.seg_tickets[seg], 1u);
+            flag[0] = (t == (unsigned int)(hi - lo) - 1u) ? seg : -1;
+            if (flag[0] >= 0) args.seg_tickets[seg] = 0u;   // ready for the next launch
+        }
     }
     __syncthreads();
     const int seg = flag[0];
     if (seg < 0) return;                                    // CTA-uniform: not the last chunk of its segment
+    if (seg & 0x100) {
+        job_publish_segment(args, seg & 0xff, (double)mine.x, (double)mine.y, flag);
+        return;
+    }
     __threadfence();
     job_fold_and_publish(args, partials, first_chunk, seg, dscratch, flag);
 }
@@ -662,37 +672,15 @@ european_job_kernel(const __grid_constant__ EuropeanParams prm, const __grid_con
     }
     block_fold2(sum, sq, scratch);
     if (threadIdx.x == 0) partials[blockIdx.x] = make_float2(sum, sq);
-    job_tail(args, partials, prm.first_chunk, dscratch, flag);
+    job_tail(args, partials, prm.first_chunk, make_float2(sum, sq), dscratch, flag);
 }
 
-// A shard that owns no chunk of a (small) job still owes its consumers +0.0 segments and its flag.
-__global__ void __launch_bounds__(kSegments)
+// A shard that owns no chunk of a (small) job still owes its consumers its flag (its segments are
+// empty, i.e. +0.0 by rule).
+__global__ void __launch_bounds__(32)
 job_publish_empty_kernel(const __grid_constant__ JobArgs args)
 {
     const int slot = (int)(args.epoch % (unsigned long long)kRing);
-    PeerMailbox *mine = args.peers.box[args.rank];
-    __shared__ int ok;
-    if (threadIdx.x == 0) {
-        ok = 1;
-        for (int c = 0; c < args.n_consumers; ++c)
-            if (args.check_acks && args.epoch > (unsigned long long)kRing &&
-                !wait_at_least(&mine->consumed[c], args.epoch - kRing, args.timeout_ns)) {
-                atomicAdd(&mine->timeouts, 1u);
-                ok = 0;
-            }
-    }
-    __syncthreads();
-    if (!ok) return;
-    const int s = args.seg_lo + (int)threadIdx.x;
-    if (s < args.seg_hi) {
-        for (int c = 0; c < args.n_consumers; ++c) {
-            double *dst = args.peers.box[c]->gather[slot] + 2 * s;
-            __stcg(dst, 0.0);
-            __stcg(dst + 1, 0.0);
-        }
-    }
-    __threadfence_system();
-    __syncthreads();
     if (threadIdx.x < (unsigned)args.n_consumers)
         *((volatile unsigned long long *)&args.peers.box[threadIdx.x]->flags[slot][args.rank]) = args.epoch;
 }
@@ -702,8 +690,8 @@ job_publish_empty_kernel(const __grid_constant__ JobArgs args)
 // then acknowledge the slot to every producer.
 __global__ void __launch_bounds__(32)
 combine_job_kernel(PeerTable peers, int rank, int world, int spin, unsigned long long epoch,
-                   unsigned long long timeout_ns, uint64_t n_paths, double discount, ResultDev *__restrict__ d_out,
-                   HostSlot *__restrict__ h_out, double *__restrict__ h_segments)
+                   unsigned long long timeout_ns, uint64_t n_chunks, uint64_t n_paths, double discount,
+                   ResultDev *__restrict__ d_out, HostSlot *__restrict__ h_out)
 {
     const int lane = threadIdx.x;
     const int slot = (int)(epoch % (unsigned long long)kRing);
@@ -717,13 +705,7 @@ combine_job_kernel(PeerTable peers, int rank, int world, int spin, unsigned long
     }
     ok = __all_sync(kFullMask, ok);
     __threadfence_system();
-    const volatile double *sg = mine->gather[slot];
-    if (h_segments) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) reinterpret_cast<volatile double *>(h_segments)[lane + 32 * i] = sg[lane + 32 * i];
-        __threadfence_system();
-    }
-    final_tree_warp(sg, lane, n_paths, discount, ok, epoch, d_out, h_out);
+    final_tree_warp(mine->gather[slot], lane, n_chunks, n_paths, discount, ok, epoch, d_out, h_out);
     __syncwarp();
     // the slot may be overwritten by job epoch + kRing once every producer sees this ack
     if (lane < world) *((volatile unsigned long long *)&peers.box[lane]->consumed[rank]) = epoch;

@@ -11,19 +11,21 @@ constexpr int kIters = 2048;
 constexpr int kIlp = 8;
 
 enum Mix { IMADW, LOP3, FFMA, EX2, LG2, SIN, SQRT, IMADW_LOP3, PHILOX_ROUND, FFMA_LOP3, FFMA_IMADW, I2F, FMNMX,
-           IMAD_HI, IMAD_LO, FFMA2, FFMA2_IMADW, EX2_IMADW, FADD2, FFMA2_LOP3, EX2_FFMA2, MIX_COUNT };
+           IMAD_HI, IMAD_LO, FFMA2, FFMA2_IMADW, EX2_IMADW, FADD2, FFMA2_LOP3, EX2_FFMA2,
+           FADD_IMADW, FMUL_IMADW, FFMA2X_IMADW, FFMA3X_IMADW, HFMA2_IMADW, FADD, FMUL, MIX_COUNT };
 const char *kNames[] = {"imad.wide.u32", "lop3", "ffma", "mufu.ex2", "mufu.lg2", "mufu.sin(+fmul.rz)", "mufu.sqrt",
                         "imad.wide+lop3 (1:1)", "philox round (2 imad.wide + 2 lop3)", "ffma+lop3 (1:1)",
                         "ffma+imad.wide (1:1)", "i2fp.u32", "fmnmx", "imad.hi.u32", "imad (lo)", "ffma2 (packed f32x2)",
                         "ffma2+imad.wide (1:1)", "mufu.ex2+imad.wide (1:1)", "fadd2", "ffma2+lop3 (1:1)",
-                        "mufu.ex2+ffma2 (1:1)"};
-const int kInstrPerStep[] = {1, 1, 1, 1, 1, 2, 1, 2, 4, 2, 2, 1, 1, 1, 1, 1, 2, 2, 1, 2, 2};
+                        "mufu.ex2+ffma2 (1:1)", "fadd+imad.wide (1:1)", "fmul+imad.wide (1:1)", "2 ffma + imad.wide",
+                        "3 ffma + imad.wide", "hfma2+imad.wide (1:1)", "fadd", "fmul"};
+const int kInstrPerStep[] = {1, 1, 1, 1, 1, 2, 1, 2, 4, 2, 2, 1, 1, 1, 1, 1, 2, 2, 1, 2, 2, 2, 2, 3, 4, 2, 1, 1};
 
 template <int MIX>
 __global__ void __launch_bounds__(1024) bench(uint32_t seed, uint32_t *out, long long *cycles)
 {
     uint32_t a[kIlp], b[kIlp];
-    float f[kIlp];
+    float f[kIlp], h[kIlp];
     unsigned long long g[kIlp];   // packed f32x2 chains
     unsigned long long gm, ga;
     asm("mov.b64 %0, {%1, %2};" : "=l"(gm) : "f"(0.999f), "f"(0.998f));
@@ -33,6 +35,7 @@ __global__ void __launch_bounds__(1024) bench(uint32_t seed, uint32_t *out, long
         a[j] = seed + threadIdx.x * 7 + j;
         b[j] = seed * 3 + threadIdx.x + j * 5;
         f[j] = 1.0f + 1e-3f * (float)(threadIdx.x + j);
+        h[j] = f[j] * 1.25f;
         asm("mov.b64 %0, {%1, %2};" : "=l"(g[j]) : "f"(f[j]), "f"(f[j] + 0.5f));
     }
     __syncthreads();
@@ -107,6 +110,23 @@ __global__ void __launch_bounds__(1024) bench(uint32_t seed, uint32_t *out, long
                 asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(f[j]));
                 asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(p) : "r"(a[j]), "r"(0xD2511F53u));
                 a[j] = (uint32_t)(p >> 32) ^ (uint32_t)p;
+            } else if (MIX == FADD_IMADW || MIX == FMUL_IMADW || MIX == FFMA2X_IMADW || MIX == FFMA3X_IMADW ||
+                       MIX == HFMA2_IMADW) {
+                uint64_t p;
+                if (MIX == FADD_IMADW) asm volatile("add.rn.f32 %0, %0, %1;" : "+f"(f[j]) : "f"(1e-3f));
+                if (MIX == FMUL_IMADW) asm volatile("mul.rn.f32 %0, %0, %1;" : "+f"(f[j]) : "f"(0.9999f));
+                if (MIX == FFMA2X_IMADW || MIX == FFMA3X_IMADW) {
+                    asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(f[j]) : "f"(0.999f), "f"(1e-3f));
+                    asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(h[j]) : "f"(0.999f), "f"(1e-3f));
+                    if (MIX == FFMA3X_IMADW) asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(f[j]) : "f"(0.998f), "f"(2e-3f));
+                }
+                if (MIX == HFMA2_IMADW) asm volatile("fma.rn.f16x2 %0, %0, %1, %2;" : "+r"(b[j]) : "r"(0x3c003c00u), "r"(0x10001000u));
+                asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(p) : "r"(a[j]), "r"(0xD2511F53u));
+                a[j] = (uint32_t)(p >> 32) ^ (uint32_t)p;
+            } else if (MIX == FADD) {
+                asm volatile("add.rn.f32 %0, %0, %1;" : "+f"(f[j]) : "f"(1e-3f));
+            } else if (MIX == FMUL) {
+                asm volatile("mul.rn.f32 %0, %0, %1;" : "+f"(f[j]) : "f"(0.9999f));
             } else if (MIX == FADD2) {
                 asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(g[j]) : "l"(ga));
             }
@@ -115,7 +135,7 @@ __global__ void __launch_bounds__(1024) bench(uint32_t seed, uint32_t *out, long
     const long long t1 = clock64();
     uint32_t acc = 0;
 #pragma unroll
-    for (int j = 0; j < kIlp; ++j) acc ^= a[j] ^ b[j] ^ __float_as_uint(f[j]) ^ (uint32_t)g[j] ^ (uint32_t)(g[j] >> 32);
+    for (int j = 0; j < kIlp; ++j) acc ^= a[j] ^ b[j] ^ __float_as_uint(f[j]) ^ __float_as_uint(h[j]) ^ (uint32_t)g[j] ^ (uint32_t)(g[j] >> 32);
     out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
     if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
 }
@@ -166,6 +186,13 @@ int main()
     run<FADD2>(sms, out, cycles);
     run<FFMA2_LOP3>(sms, out, cycles);
     run<EX2_FFMA2>(sms, out, cycles);
+    run<FADD_IMADW>(sms, out, cycles);
+    run<FMUL_IMADW>(sms, out, cycles);
+    run<FFMA2X_IMADW>(sms, out, cycles);
+    run<FFMA3X_IMADW>(sms, out, cycles);
+    run<HFMA2_IMADW>(sms, out, cycles);
+    run<FADD>(sms, out, cycles);
+    run<FMUL>(sms, out, cycles);
     cudaError_t err = cudaDeviceSynchronize();
     printf("status: %s\n", cudaGetErrorString(err));
     return err != cudaSuccess;
