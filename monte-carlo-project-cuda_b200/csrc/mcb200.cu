@@ -383,41 +383,6 @@ __global__ void curand_blocks_kernel(uint64_t seed, const uint64_t *__restrict__
     out[i] = curand4(&s);
 }
 
-// ---- TMA tensor maps for the fast slab kernel ----------------------------------------------------
-// The driver's encoder is reached through the runtime (no link against libcuda).
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn tensor_map_encoder()
-{
-    static EncodeTiledFn fn = []() -> EncodeTiledFn {
-        void *p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
-            q != cudaDriverEntryPointSuccess) {
-            cudaGetLastError();
-            return nullptr;
-        }
-        return reinterpret_cast<EncodeTiledFn>(p);
-    }();
-    return fn;
-}
-
-// The output array seen as [lines][16] 4-byte elements (64-byte lines); a box is one slab.
-bool encode_slab_map(CUtensorMap *map, void *base, uint64_t total_elems, uint32_t slab_elems, bool is_int)
-{
-    EncodeTiledFn enc = tensor_map_encoder();
-    if (!enc || !base) return false;
-    const cuuint64_t dims[2] = {16, total_elems / 16};
-    const cuuint64_t strides[1] = {64};
-    const cuuint32_t box[2] = {16, slab_elems / 16};
-    const cuuint32_t estr[2] = {1, 1};
-    return enc(map, is_int ? CU_TENSOR_MAP_DATA_TYPE_INT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box,
-               estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
 // Tuning knobs of the trajectory launcher (tools/traj_bench.py sweeps them through the environment;
 // unset = the shipped configuration).
 int env_int(const char *name, int dflt)
@@ -426,7 +391,7 @@ int env_int(const char *name, int dflt)
     return v && *v ? atoi(v) : dflt;
 }
 
-// One row layout (SPL steps per lane, LPR lanes per row): the TMA slab kernels when the row fits one
+// One row layout (SPL steps per lane, LPR lanes per row): the TMA slab kernel when the row fits one
 // pass and is 16-byte aligned (the bandwidth path, config 3; counts and log2 prices ride along in
 // their own staging rows), the general kernel otherwise.
 template <int SPL, int LPR>
@@ -435,9 +400,7 @@ void launch_trajectory(const PathParams &prm_in, uint64_t n_paths, bool vec, boo
 {
     constexpr int kRowsPerWarp = 32 / LPR;
     constexpr int kSlabWarps = 4;
-    PathParams prm = prm_in;
-    SlabTensorMaps maps{};
-    uint64_t grid_cap = 0;
+    const PathParams &prm = prm_in;
     // rows longer than one pass: one row group per slab, the whole rows staged -- while the staging
     // leaves enough CTAs per SM (measured on 2^20 rows: prices only 4.07 TB/s at 1024 steps / 32 KB,
     // 3.67 at 1536 / 48 KB, then the general kernel's 3.5 TB/s wins; with counts the general
@@ -449,14 +412,11 @@ void launch_trajectory(const PathParams &prm_in, uint64_t n_paths, bool vec, boo
     do {                                                                                                      \
         auto kern = trajectory_slab_kernel<SPL, LPR, ROWS, WARPS, CNT, LOG, MULTI, ALIGNED, FAST>;            \
         const uint64_t rows_per_cta = (uint64_t)(WARPS) * (ROWS);                                             \
-        uint64_t ctas = (prm.n_paths + rows_per_cta - 1) / rows_per_cta;                                      \
-        if (grid_cap && ctas > grid_cap) ctas = grid_cap;   /* persistent: warps stride over the slabs */     \
-        const size_t per_array = ((FAST) & kFastSwizzle)                                                      \
-                                     ? ((((size_t)(ROWS) * (size_t)prm.n_steps + 127) & ~(size_t)127))        \
-                                     : (size_t)(ROWS) * (size_t)prm.n_steps;                                  \
-        const size_t smem = (size_t)(WARPS) * (1 + (CNT ? 1 : 0) + (LOG ? 1 : 0)) * per_array * sizeof(float); \
+        const uint64_t ctas = (n_paths + rows_per_cta - 1) / rows_per_cta;                                    \
+        const size_t smem = (size_t)(WARPS) * (1 + (CNT ? 1 : 0) + (LOG ? 1 : 0)) * (ROWS) *                  \
+                            (size_t)prm.n_steps * sizeof(float);                                              \
         if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        kern<<<(unsigned)ctas, (WARPS) * 32, smem, st>>>(prm, d_prices, d_counts, d_logs, maps);              \
+        kern<<<(unsigned)ctas, (WARPS) * 32, smem, st>>>(prm, d_prices, d_counts, d_logs);                    \
     } while (0)
 #define MCB_SLAB(ROWS, CNT, LOG, MULTI, ALIGNED) MCB_SLAB_W(ROWS, CNT, LOG, MULTI, ALIGNED, false, kSlabWarps)
     // (only the largest layout is ever asked for rows longer than its pass)
@@ -468,65 +428,19 @@ void launch_trajectory(const PathParams &prm_in, uint64_t n_paths, bool vec, boo
             else MCB_SLAB(kRowsPerWarp, false, false, true, true);
         }
     } else if (vec && prm.n_steps <= SPL * LPR) {
-        // The fast variants (bit mask: 1 hoisted Philox products, 2 packed FP32x2, 4 swizzled staging + one TMA
-        // tensor store per array) take every whole slab of 4 rows (4 * n_steps floats are whole 64-byte
-        // lines because n_steps % 4 == 0); a ragged tail of up to 3 rows goes to the linear slab kernel below.
-        constexpr int kFastRows = 4;
-        static_assert(kFastRows % kRowsPerWarp == 0, "a slab is a whole number of passes");
-        const uint64_t fast_paths = n_paths / kFastRows * kFastRows;
-        const uint64_t total = fast_paths * (uint64_t)prm.n_steps;
-        // shipped choice: arrays beyond the prices (barrier counts, log2 prices) -> all three; prices only ->
-        // the linear kernel (measured, profiles/r2_trajectory_tuning.txt).  MCB_TRAJ_MODE overrides (tools/).
-        const int mode = env_int("MCB_TRAJ_MODE", n_arrays > 1 ? kFastAll : 0);
-        bool fast = mode != 0 && fast_paths > 0 && total / 16 < 0x7fffffffull;
-        if (fast && (mode & kFastSwizzle)) {
-            fast = encode_slab_map(&maps.prices, d_prices, total, kFastRows * (uint32_t)prm.n_steps, false);
-            if (fast && d_counts) fast = encode_slab_map(&maps.counts, d_counts, total, kFastRows * (uint32_t)prm.n_steps, true);
-            if (fast && d_logs) fast = encode_slab_map(&maps.logs, d_logs, total, kFastRows * (uint32_t)prm.n_steps, false);
-        }
-        if (fast) {
-            prm.n_paths = fast_paths;
-            grid_cap = (uint64_t)env_int("MCB_TRAJ_CTAS_PER_SM", 0) * 148ull;
-#define MCB_FAST(F)                                                                                            \
-            do {                                                                                               \
-                if (d_counts && d_logs) MCB_SLAB_W(kFastRows, true, true, false, true, F, kSlabWarps);         \
-                else if (d_counts) MCB_SLAB_W(kFastRows, true, false, false, true, F, kSlabWarps);             \
-                else if (d_logs) MCB_SLAB_W(kFastRows, false, true, false, true, F, kSlabWarps);               \
-                else MCB_SLAB_W(kFastRows, false, false, false, true, F, kSlabWarps);                          \
-            } while (0)
-            bool launched = true;
-            if (mode == kFastAll) MCB_FAST(kFastAll);
-            else if constexpr (SPL * LPR == 256) {   // the partial combinations exist for the tuning sweep only
-                if (mode == 1) MCB_FAST(1);
-                else if (mode == 4) MCB_FAST(4);
-                else if (mode == 5) MCB_FAST(5);
-                else if (mode == 3) MCB_FAST(3);
-                else launched = false;
-            } else launched = false;
-#undef MCB_FAST
-            grid_cap = 0;
-            if (launched) {
-                // the tail: rows [fast_paths, n_paths) through the linear kernel
-                prm.first_path = prm_in.first_path + fast_paths;
-                prm.n_paths = n_paths - fast_paths;
-                const uint64_t off = fast_paths * (uint64_t)prm.n_steps;
-                d_prices += off;
-                if (d_counts) d_counts += off;
-                if (d_logs) d_logs += off;
-            } else {
-                prm.n_paths = n_paths;
-            }
-        }
         // rows per slab: ~6 for one output array (tuned on B200 at 2^20 x 252, profiles/r1_trajectory_tuning.txt),
         // fewer when counts / logs need their own staging rows; always a whole number of passes
         constexpr int kRows1 = (6 + kRowsPerWarp - 1) / kRowsPerWarp * kRowsPerWarp;
         constexpr int kRows2 = (4 + kRowsPerWarp - 1) / kRowsPerWarp * kRowsPerWarp;
         constexpr int kRows3 = (2 + kRowsPerWarp - 1) / kRowsPerWarp * kRowsPerWarp;
-        if (prm.n_paths == 0) {
-        } else if (d_counts && d_logs) MCB_SLAB(kRows3, true, true, false, true);
-        else if (d_counts) MCB_SLAB(kRows2, true, false, false, true);
-        else if (d_logs) MCB_SLAB(kRows2, false, true, false, true);
-        else MCB_SLAB(kRows1, false, false, false, true);
+        // hoisted Philox products + packed FP32x2 (the kernel's FAST flag) pay when more than the prices is
+        // stored (prices + counts 354 -> 345 us) and not for prices alone (250 -> 251 us); MCB_TRAJ_FAST
+        // overrides for tools/traj_bench.py
+        const bool fast = env_int("MCB_TRAJ_FAST", n_arrays > 1 ? 1 : 0) != 0;
+        if (d_counts && d_logs) { if (fast) MCB_SLAB_W(kRows3, true, true, false, true, true, kSlabWarps); else MCB_SLAB(kRows3, true, true, false, true); }
+        else if (d_counts) { if (fast) MCB_SLAB_W(kRows2, true, false, false, true, true, kSlabWarps); else MCB_SLAB(kRows2, true, false, false, true); }
+        else if (d_logs) { if (fast) MCB_SLAB_W(kRows2, false, true, false, true, true, kSlabWarps); else MCB_SLAB(kRows2, false, true, false, true); }
+        else { if (fast) MCB_SLAB_W(kRows1, false, false, false, true, true, kSlabWarps); else MCB_SLAB(kRows1, false, false, false, true); }
     } else if (base_aligned && prm.n_steps <= SPL * LPR) {
         // rows that are not a multiple of 4 floats (150, 250 steps ...): slabs of 8 / 4 rows start on
         // 16-byte boundaries, so the bulk store still applies; only the staging is element-wise

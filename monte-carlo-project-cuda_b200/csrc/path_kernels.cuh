@@ -6,7 +6,6 @@
 //   compute_nmc_one_block_per_point / _with_outter / compute_nmc_optimal   inc/nmc.cuh:12-386
 #pragma once
 #include <cstdint>
-#include <cuda.h>   // CUtensorMap (type only; the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cuda_runtime.h>
 
 #include "block_reduce.cuh"
@@ -319,41 +318,27 @@ trajectory_kernel(const __grid_constant__ PathParams prm, float *__restrict__ pr
 // Otherwise (150- or 250-step rows ...) the lanes stage element by element, ROWS is a multiple
 // of 4 so that every SLAB still starts on a 16-byte boundary of the output, the bulk store takes
 // the slab's whole 16-byte units and one lane writes the last one to three floats of a ragged slab.
-// FAST (one-pass, 16-byte aligned rows only): the three issue-slot savers together --
-//   * the lane-invariant Philox products hoisted out of the row loop (RowHoist),
-//   * Box-Muller and the base add in packed FP32x2 instructions,
-//   * conflict-free staging: the lanes' STS.128 at a 64-byte lane stride hit two bank groups (4-way
-//     conflict, 70 % of the kernel's shared-memory wavefronts, which queue in the same MIO pipe the
-//     MUFU instructions need); the slab is staged with TMA's 64-byte swizzle (address bits 4-5 ^= bits
-//     7-8: every quarter-warp then covers all eight 16-byte bank groups) and leaves through ONE
-//     cp.async.bulk.tensor store per array that un-swizzles on the way out.  The output is described to
-//     TMA as a [total/16][16] float tensor, so slabs only need to be whole 64-byte lines:
-//     ROWS * n_steps % 16 == 0 (the host picks ROWS and sends a ragged tail to the linear kernel).
-struct SlabTensorMaps {
-    CUtensorMap prices, counts, logs;
-};
-
-__device__ __forceinline__ void tensor_store_2d(void *smem, const CUtensorMap *map, int c0, int c1)
-{
-    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-                 :: "l"(map), "r"(smem_addr(smem)), "r"(c0), "r"(c1) : "memory");
-}
-
-enum { kFastHoist = 1, kFastPack = 2, kFastSwizzle = 4, kFastAll = 7 };
-
+// FAST (one-pass, 16-byte aligned rows): the lane-invariant Philox products hoisted out of the row loop
+// (RowHoist: 16.5 instead of 18.75 IMAD.WIDE per block) and Box-Muller + the base add in packed FP32x2
+// instructions (28 fewer issue slots per pass).  Same bits as the plain form.  Measured on 2^20 x 252
+// (profiles/r2_trajectory_tuning.txt): prices + counts 354 -> 345 us (6.12 TB/s); prices only 250 -> 251 us,
+// so the launcher uses it when counts / log2 prices are stored next to the prices.  (Conflict-free
+// staging -- TMA's 64-byte swizzle + one cp.async.bulk.tensor store per slab -- was also built and
+// measured: shared-memory bank conflicts 25.9 M -> 0.9 M, wavefronts 36.9 M -> 11.8 M, and NO gain, 255-266 us:
+// the conflicts were never the limiter; that variant is not shipped.)
 template <int SPL, int LPR, int ROWS, int WARPS, bool COUNTS, bool LOGS, bool MULTI = false, bool ALIGNED = true,
-          int FAST = 0>
+          bool FAST = false>
 __global__ void __launch_bounds__(WARPS * 32)
 trajectory_slab_kernel(const __grid_constant__ PathParams prm, float *__restrict__ prices, int *__restrict__ counts,
-                       float *__restrict__ logs, const __grid_constant__ SlabTensorMaps maps)
+                       float *__restrict__ logs)
 {
-    static_assert(!FAST || (ALIGNED && !MULTI), "the fast path is for one-pass, 16-byte aligned rows");
+    static_assert(!FAST || (ALIGNED && !MULTI), "the hoisted products assume one pass per row, the packed stores aligned rows");
     constexpr int kBlocks = SPL / 4;
     constexpr int kRowsPerWarp = 32 / LPR;
     constexpr int kArrays = 1 + (COUNTS ? 1 : 0) + (LOGS ? 1 : 0);
     static_assert(ROWS % kRowsPerWarp == 0, "a slab is a whole number of passes");
     static_assert(ALIGNED || ROWS % 4 == 0, "unaligned rows: slabs must start on 16-byte boundaries");
-    extern __shared__ __align__(1024) float stage[];   // [warp][array][ROWS][n_steps] (FAST: each array 512-byte aligned)
+    extern __shared__ __align__(128) float stage[];    // [warp][array][ROWS][n_steps]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sub = lane / LPR, ln = lane % LPR;
     const int n_steps = prm.n_steps;
@@ -361,12 +346,11 @@ trajectory_slab_kernel(const __grid_constant__ PathParams prm, float *__restrict
     const uint32_t n_slabs = (n_rows + ROWS - 1) / ROWS;
     const uint32_t slab_stride = gridDim.x * WARPS;   // a warp strides over the slabs (one each when the grid covers them)
     const int lane_step = SPL * ln;
-    // floats between the arrays of a slab in shared memory: dense, or rounded up to the swizzle period
-    const int slab_floats = (FAST & kFastSwizzle) ? ((ROWS * n_steps + 127) & ~127) : ROWS * n_steps;
+    const int slab_floats = ROWS * n_steps;
     float *my_stage = stage + (size_t)warp * kArrays * slab_floats;
     float *dst0 = my_stage + sub * n_steps + lane_step;
     RowHoist<SPL> hoist;
-    if (FAST & kFastHoist) hoist = make_row_hoist<SPL>(prm, (uint32_t)(prm.first_path >> 32), lane_step);
+    if (FAST) hoist = make_row_hoist<SPL>(prm, (uint32_t)(prm.first_path >> 32), lane_step);
 
 #pragma unroll 1
     for (uint32_t slab = blockIdx.x * WARPS + warp; slab < n_slabs; slab += slab_stride) {
@@ -385,12 +369,12 @@ trajectory_slab_kernel(const __grid_constant__ PathParams prm, float *__restrict
                 const int my_step = step0 + lane_step;
                 const bool active = my_step < n_steps;
                 PassWords<SPL> words;
-                if ((FAST & kFastHoist) && (uint32_t)(p >> 32) == hoist.p_hi)
+                if (FAST && (uint32_t)(p >> 32) == hoist.p_hi)
                     words = row_words_hoisted<SPL>(prm, hoist, (uint32_t)p);
                 else words = row_words<SPL>(prm, (uint32_t)p, (uint32_t)(p >> 32), my_step);
                 float a[SPL];
-                const float base = row_finish<SPL, LPR, (FAST & kFastPack) != 0>(prm, words, active, carry_l, a);
-                if (FAST & kFastPack) {                                      // log2 prices of this lane's steps
+                const float base = row_finish<SPL, LPR, FAST>(prm, words, active, carry_l, a);
+                if (FAST) {                                                  // log2 prices of this lane's steps
                     const uint64_t bb = f2_pack(base, base);
 #pragma unroll
                     for (int j = 0; j < SPL; j += 2) f2_unpack(f2_add(f2_pack(a[j], a[j + 1]), bb), a[j], a[j + 1]);
@@ -425,16 +409,7 @@ trajectory_slab_kernel(const __grid_constant__ PathParams prm, float *__restrict
                                 c[j] = cbase;
                             }
                         }
-                        if (FAST & kFastSwizzle) {
-                            // 64-byte swizzle on the slab-linear offset: 16-byte unit index ^= (offset >> 7) & 3
-                            const uint32_t lin = (uint32_t)((r + sub) * n_steps + lane_step + 4 * b) * 4u;
-                            float *sw = my_stage + ((lin ^ ((lin >> 3) & 0x30u)) >> 2);
-                            if (COUNTS) *reinterpret_cast<int4 *>(sw + slab_floats) = make_int4(c[0], c[1], c[2], c[3]);
-                            if (LOGS)
-                                *reinterpret_cast<float4 *>(sw + (COUNTS ? 2 : 1) * slab_floats) =
-                                    make_float4(a[4 * b], a[4 * b + 1], a[4 * b + 2], a[4 * b + 3]);
-                            *reinterpret_cast<float4 *>(sw) = make_float4(s4[0], s4[1], s4[2], s4[3]);
-                        } else if (ALIGNED) {
+                        if (ALIGNED) {
                             if (COUNTS)
                                 *reinterpret_cast<int4 *>(dst + slab_floats + 4 * b) = make_int4(c[0], c[1], c[2], c[3]);
                             if (LOGS)
@@ -457,16 +432,7 @@ trajectory_slab_kernel(const __grid_constant__ PathParams prm, float *__restrict
         }
         fence_async_smem();   // generic-proxy STS -> visible to the async proxy (TMA)
         __syncwarp();
-        if (FAST & kFastSwizzle) {
-            // the host launches this variant on whole slabs only; ONE tensor store per array un-swizzles
-            if (lane == 0) {
-                const int line = (int)(((uint64_t)slab_row * (uint32_t)n_steps) >> 4);   // 64-byte line of the slab
-                tensor_store_2d(my_stage, &maps.prices, 0, line);
-                if (COUNTS) tensor_store_2d(my_stage + slab_floats, &maps.counts, 0, line);
-                if (LOGS) tensor_store_2d(my_stage + (COUNTS ? 2 : 1) * slab_floats, &maps.logs, 0, line);
-                bulk_commit();
-            }
-        } else if (lane == 0) {
+        if (lane == 0) {
             const uint32_t rows = min((uint32_t)ROWS, n_rows - slab_row);
             const uint32_t floats = rows * (uint32_t)n_steps;
             const uint32_t bytes = ALIGNED ? floats * 4u : (floats * 4u) & ~15u;   // whole 16-byte units

@@ -1,10 +1,9 @@
 """Times the trajectory kernels (2^20 rows, device buffer) with CUDA events and checks that every launcher
 variant writes the same bits:  python tools/traj_bench.py [steps ...]   (default 252)
 
-Variants are selected through the launcher's environment knobs (csrc/mcb200.cu launch_trajectory):
-MCB_TRAJ_MODE = 0 the linear slab kernel (round 1), else a bit mask of the fast kernel's features (1 hoisted
-Philox products, 2 packed FP32x2, 4 swizzled staging + TMA tensor store); MCB_TRAJ_CTAS_PER_SM caps the grid
-(persistent warps striding over the slabs, which amortises the hoisted products)."""
+The slab kernel's FAST flag (hoisted Philox products + packed FP32x2) is forced on / off through the
+launcher's MCB_TRAJ_FAST knob (csrc/mcb200.cu launch_trajectory); unset, the launcher uses it when counts or
+log2 prices are stored next to the prices."""
 import os
 import sys
 
@@ -40,10 +39,8 @@ for steps in steps_list:
     opt = pkg.option(N_STEPS=steps, N_PATHS=n, B=120.0)
     for want_counts in (False, True):
         ref = None
-        # mode bits: 1 hoisted Philox products, 2 packed FP32x2, 4 swizzled staging + TMA tensor store
-        for mode, per_sm in ((0, 0), (1, 0), (3, 0), (4, 0), (5, 0), (7, 0), (1, 9), (5, 9), (7, 9), (7, 18)):
-            os.environ["MCB_TRAJ_MODE"] = str(mode)
-            os.environ["MCB_TRAJ_CTAS_PER_SM"] = str(per_sm)
+        for fast in (0, 1):   # the slab kernel's FAST flag: hoisted Philox products + packed FP32x2
+            os.environ["MCB_TRAJ_FAST"] = str(fast)
             buf = torch.full((n * steps,), float("nan"), dtype=torch.float32, device="cuda")
             cnt = torch.full((n * steps,), -1, dtype=torch.int32, device="cuda") if want_counts else None
             ms = run(opt, buf, cnt)
@@ -55,9 +52,8 @@ for steps in steps_list:
                 ok = bool((buf.view(torch.int32) == ref[0].view(torch.int32)).all())
                 if cnt is not None:
                     ok = ok and bool((cnt == ref[1]).all())
-                same = "bits==mode0" if ok else "BITS DIFFER"
-            print(f"steps={steps} counts={int(want_counts)} mode={mode} ctas/SM={per_sm or 'all'}: {ms*1e3:7.1f} us  "
+                same = "bits==plain" if ok else "BITS DIFFER"
+            print(f"steps={steps} counts={int(want_counts)} fast={fast}: {ms*1e3:7.1f} us  "
                   f"{per*n*steps/ms/1e6:7.1f} GB/s  {same}", flush=True)
             del buf, cnt
-os.environ.pop("MCB_TRAJ_MODE", None)
-os.environ.pop("MCB_TRAJ_CTAS_PER_SM", None)
+os.environ.pop("MCB_TRAJ_FAST", None)
