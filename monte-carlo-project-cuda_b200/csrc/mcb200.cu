@@ -341,8 +341,14 @@ int launch_european(mcb_engine *e, const EuropeanParams &prm, int option_type, u
 int launch_segments(mcb_engine *e, const float2 *partials, uint64_t stride, uint64_t first_chunk, uint64_t n_chunks,
                     int seg_lo, int seg_hi, int n_sets, double *d_segments, cudaStream_t st, int write_unowned = 1)
 {
-    segment_kernel<<<dim3(MCB_SEGMENTS, (unsigned)n_sets), kSlots, 0, st>>>(partials, stride, first_chunk, n_chunks,
-                                                                           seg_lo, seg_hi, write_unowned, d_segments);
+    if (n_sets >= 8) {   // many small folds (the sweep): one warp per (set, segment), same tree
+        const uint64_t items = (uint64_t)n_sets * MCB_SEGMENTS;
+        segment_sets_kernel<<<(unsigned)((items + kWarps - 1) / kWarps), kSlots, 0, st>>>(
+            partials, stride, first_chunk, n_chunks, seg_lo, seg_hi, write_unowned, n_sets, d_segments);
+    } else {
+        segment_kernel<<<dim3(MCB_SEGMENTS, (unsigned)n_sets), kSlots, 0, st>>>(partials, stride, first_chunk, n_chunks,
+                                                                               seg_lo, seg_hi, write_unowned, d_segments);
+    }
     e->launches++;
     CU(cudaGetLastError());
     return MCB_OK;
@@ -1303,14 +1309,25 @@ static int sweep_segments_impl(mcb_engine *e, const mcb_option_data *opt, const 
     for (uint64_t i0 = 0; i0 < (uint64_t)n_params; i0 += group) {
         const uint64_t cnt = (uint64_t)n_params - i0 < group ? (uint64_t)n_params - i0 : group;
         prm.n_sets = (int)cnt;
-        // A rank that owns fewer than ~3 waves of chunks (2 CTAs resident per SM at 128 registers) loses
-        // its last, partly filled wave: halving the sets per CTA over gridDim.y doubles the CTA count
-        // (measured at 512 chunks x 1024 sets: 2.71 -> 2.37 ms; finer splits and larger grids gain nothing)
-        const uint64_t wave = 2ull * (uint64_t)e->prop.multiProcessorCount;
-        uint64_t splits = (local && local < 3 * wave) ? 2 : 1;
-        if (splits > (cnt + 63) / 64) splits = (cnt + 63) / 64;
-        if (splits < 1) splits = 1;
-        prm.sets_per_cta = (int)(((cnt + splits - 1) / splits + kSweepTile - 1) / kSweepTile * kSweepTile);
+        // How many ways to split the sets over gridDim.y: a CTA costs one draw of its chunk (~57 instructions
+        // per path, about 10.5 (path, set) units of the MUFU-bound loop) plus its sets, and the grid runs in
+        // whole waves of 2 CTAs per SM (128 registers).  More splits repeat the draw but fill the last wave:
+        // 512 chunks x 1024 sets on 148 SMs -> 4 splits (6.92 waves of 256-set CTAs) instead of 2 (3.46 waves).
+        const uint64_t slots = 2ull * (uint64_t)e->prop.multiProcessorCount;
+        uint64_t best_sets = (cnt + kSweepTile - 1) / kSweepTile * kSweepTile;
+        double best_cost = 1e300;
+        for (uint64_t y : {1ull, 2ull, 3ull, 4ull, 6ull, 8ull}) {
+            if (y > 1 && cnt / y < 64) break;
+            const uint64_t per = ((cnt + y - 1) / y + kSweepTile - 1) / kSweepTile * kSweepTile;
+            const uint64_t gy = (cnt + per - 1) / per;
+            const uint64_t waves = local ? (local * gy + slots - 1) / slots : 0;
+            const double cost = (double)waves * (10.5 + (double)per);
+            if (cost < best_cost * 0.995) {
+                best_cost = cost;
+                best_sets = per;
+            }
+        }
+        prm.sets_per_cta = (int)best_sets;
         const unsigned grid_y = (unsigned)((cnt + (uint64_t)prm.sets_per_cta - 1) / (uint64_t)prm.sets_per_cta);
         if (local) {
             TimedScope timed(e, MCB_KERNEL_SWEEP, st);

@@ -183,6 +183,12 @@ __device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b)
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
     return r;
 }
+__device__ __forceinline__ uint64_t f2_sub(uint64_t a, uint64_t b)
+{
+    uint64_t r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
 
 // increments4 with the two Box-Muller pairs of a block worked side by side: 5 packed instructions
 // (2 FFMA2 uniform maps, 1 FMUL2 radius scale, 2 FFMA2 increments) instead of 10 scalar ones.

@@ -153,32 +153,39 @@ sweep_kernel(const __grid_constant__ SweepParams prm, const float4 *__restrict__
     const int set_end = min(prm.n_sets, set_begin + prm.sets_per_cta);
     for (int s0 = set_begin; s0 < set_end; s0 += kSweepTile) {
         float sum[kSweepTile], sq[kSweepTile];
+        // Two parameter sets ride in one packed FP32x2 register pair: per (path, pair of sets)
+        //   FFMA2, 2 x MUFU.EX2, FADD2, 2 x FMNMX, FADD2, FFMA2
+        // = 4 issue slots per (path, set) instead of 6, so the schedulers keep the XU pipe (one EX2 per
+        // unit, 8 clk per warp instruction) fed.  Every half rounds like the scalar instruction of
+        // european_kernel: same bits.
 #pragma unroll
-        for (int k = 0; k < kSweepTile; ++k) {
-            sum[k] = 0.0f;
-            sq[k] = 0.0f;
-            if (s0 + k < set_end) {
-                const float4 c = __ldg(sets + s0 + k);
-                if (n_valid == PPS) {
+        for (int k = 0; k < kSweepTile; k += 2) {
+            const bool have0 = s0 + k < set_end, have1 = s0 + k + 1 < set_end;
+            const float4 ca = have0 ? __ldg(sets + s0 + k) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            const float4 cb = have1 ? __ldg(sets + s0 + k + 1) : ca;
+            const uint64_t cx = f2_pack(ca.x, cb.x), cy = f2_pack(ca.y, cb.y), ck = f2_pack(ca.z, cb.z);
+            uint64_t acc = f2_pack(0.0f, 0.0f), acq = f2_pack(0.0f, 0.0f);
+            auto one_path = [&](float z) {
+                float l0, l1, d0, d1;
+                f2_unpack(f2_fma(cy, f2_pack(z, z), cx), l0, l1);
+                const uint64_t st = f2_pack(mufu_ex2(l0), mufu_ex2(l1));
+                f2_unpack(TYPE == kPut ? f2_sub(ck, st) : f2_sub(st, ck), d0, d1);
+                const uint64_t pay = f2_pack(fmaxf(d0, 0.0f), fmaxf(d1, 0.0f));
+                acc = f2_add(acc, pay);
+                acq = f2_fma(pay, pay, acq);
+            };
+            if (n_valid == PPS) {            // every chunk but a ragged last one: straight-line code
 #pragma unroll
-                    for (int i = 0; i < PPS; ++i) {
-                        const float St = mufu_ex2(fmaf(c.y, unit[i], c.x));
-                        const float pay = TYPE == kPut ? fmaxf(c.z - St, 0.0f) : fmaxf(St - c.z, 0.0f);
-                        sum[k] = sum[k] + pay;
-                        sq[k] = fmaf(pay, pay, sq[k]);
-                    }
-                } else {
+                for (int i = 0; i < PPS; ++i) one_path(unit[i]);
+            } else {
 #pragma unroll
-                    for (int i = 0; i < PPS; ++i) {
-                        if (i < n_valid) {
-                            const float St = mufu_ex2(fmaf(c.y, unit[i], c.x));
-                            const float pay = TYPE == kPut ? fmaxf(c.z - St, 0.0f) : fmaxf(St - c.z, 0.0f);
-                            sum[k] = sum[k] + pay;
-                            sq[k] = fmaf(pay, pay, sq[k]);
-                        }
-                    }
-                }
+                for (int i = 0; i < PPS; ++i)
+                    if (i < n_valid) one_path(unit[i]);
             }
+            f2_unpack(acc, sum[k], sum[k + 1]);
+            f2_unpack(acq, sq[k], sq[k + 1]);
+            if (!have0) sum[k] = sq[k] = 0.0f;
+            if (!have1) sum[k + 1] = sq[k + 1] = 0.0f;
         }
         // same tree as block_fold2, kSweepTile parameter sets at a time
 #pragma unroll
@@ -408,6 +415,54 @@ combine_kernel(const double *__restrict__ segments, uint64_t n_paths, double dis
         r.sumsq = q;
         r.n_paths = n_paths;
         out[set] = r;
+    }
+}
+
+// The same segment pass for MANY parameter sets (the sweep: 1024 sets x 64 segments = 65 536 folds of a few
+// dozen partials each): one WARP per (set, segment) instead of one CTA, walking the eight "virtual warps"
+// of segment_kernel's 256-slot tree one after the other -- the same additions in the same order, so the
+// same bits, with an eighth of the CTAs and no barrier.
+__global__ void __launch_bounds__(kSlots)
+segment_sets_kernel(const float2 *__restrict__ partials, uint64_t partials_stride, uint64_t partials_first_chunk,
+                    uint64_t n_chunks, int seg_lo, int seg_hi, int write_unowned, int n_sets,
+                    double *__restrict__ segments)
+{
+    const int lane = threadIdx.x & 31;
+    const uint64_t item = (uint64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
+    if (item >= (uint64_t)n_sets * kSegments) return;                  // warp-uniform
+    const int set = (int)(item / kSegments), seg = (int)(item % kSegments);
+    const bool owned = seg >= seg_lo && seg < seg_hi;
+    if (!owned && !write_unowned) return;
+    double ta = 0.0, tb = 0.0;                                          // lane v < 8: total of virtual warp v
+    if (owned) {
+        const uint64_t lo = (n_chunks * (uint64_t)seg) / kSegments;
+        const uint64_t hi = (n_chunks * (uint64_t)(seg + 1)) / kSegments;
+        const float2 *src = partials + (uint64_t)set * partials_stride;
+        for (int v = 0; v < kWarps; ++v) {
+            if (lo + (uint64_t)(32 * v) >= hi) break;                   // the remaining slots are all +0.0
+            double a = 0.0, b = 0.0;
+            for (uint64_t c = lo + (uint64_t)(32 * v + lane); c < hi; c += kSlots) {
+                const float2 p = src[c - partials_first_chunk];
+                a = a + (double)p.x;
+                b = b + (double)p.y;
+            }
+            a = __shfl_sync(kFullMask, warp_fold(a), 0);
+            b = __shfl_sync(kFullMask, warp_fold(b), 0);
+            if (lane == v) {
+                ta = a;
+                tb = b;
+            }
+        }
+    }
+#pragma unroll
+    for (int off = kWarps / 2; off > 0; off >>= 1) {                    // block_fold2's 8 -> 1 step
+        ta = ta + __shfl_down_sync(kFullMask, ta, off);
+        tb = tb + __shfl_down_sync(kFullMask, tb, off);
+    }
+    if (lane == 0) {
+        double *dst = segments + ((uint64_t)set * kSegments + seg) * 2;
+        dst[0] = ta;
+        dst[1] = tb;
     }
 }
 
