@@ -63,8 +63,8 @@ class OptionData(C.Structure):
 def option(S0=100.0, T=1.0, K=100.0, r=0.05, v=0.2, B=120.0, P1=10, P2=50, N_PATHS=1 << 20,
            N_PATHS_INNER=1000, N_STEPS=1, step=None) -> OptionData:
     """BASELINE config-1 parameters by default; ``step`` = T/N_STEPS in float as hello.cu:17."""
-    if step is None:
-        step = float(np.float32(T) / np.float32(N_STEPS))
+    if step is None:   # N_STEPS <= 0 is an invalid option the engine rejects: leave step at 0 instead of dividing
+        step = float(np.float32(T) / np.float32(N_STEPS)) if N_STEPS > 0 else 0.0
     return OptionData(S0, T, K, r, v, B, P1, P2, N_PATHS, N_PATHS_INNER, N_STEPS, step)
 
 

@@ -439,10 +439,10 @@ void launch_trajectory(const PathParams &prm_in, uint64_t n_paths, bool vec, boo
         constexpr int kRows1 = (6 + kRowsPerWarp - 1) / kRowsPerWarp * kRowsPerWarp;
         constexpr int kRows2 = (4 + kRowsPerWarp - 1) / kRowsPerWarp * kRowsPerWarp;
         constexpr int kRows3 = (2 + kRowsPerWarp - 1) / kRowsPerWarp * kRowsPerWarp;
-        // hoisted Philox products + packed FP32x2 (the kernel's FAST flag) pay when more than the prices is
-        // stored (prices + counts 354 -> 345 us) and not for prices alone (250 -> 251 us); MCB_TRAJ_FAST
-        // overrides for tools/traj_bench.py
-        const bool fast = env_int("MCB_TRAJ_FAST", n_arrays > 1 ? 1 : 0) != 0;
+        // hoisted Philox products + packed FP32x2 (the kernel's FAST flag): 2^20 x 252 prices 250 -> 238 us,
+        // prices + counts 354 -> 344 us, same bits (profiles/r2_trajectory_tuning.txt); MCB_TRAJ_FAST=0 is
+        // the plain form, kept for tools/traj_bench.py's A/B run
+        const bool fast = env_int("MCB_TRAJ_FAST", 1) != 0;
         if (d_counts && d_logs) { if (fast) MCB_SLAB_W(kRows3, true, true, false, true, true, kSlabWarps); else MCB_SLAB(kRows3, true, true, false, true); }
         else if (d_counts) { if (fast) MCB_SLAB_W(kRows2, true, false, false, true, true, kSlabWarps); else MCB_SLAB(kRows2, true, false, false, true); }
         else if (d_logs) { if (fast) MCB_SLAB_W(kRows2, false, true, false, true, true, kSlabWarps); else MCB_SLAB(kRows2, false, true, false, true); }

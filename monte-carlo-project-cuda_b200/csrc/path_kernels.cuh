@@ -321,11 +321,10 @@ trajectory_kernel(const __grid_constant__ PathParams prm, float *__restrict__ pr
 // FAST (one-pass, 16-byte aligned rows): the lane-invariant Philox products hoisted out of the row loop
 // (RowHoist: 16.5 instead of 18.75 IMAD.WIDE per block) and Box-Muller + the base add in packed FP32x2
 // instructions (28 fewer issue slots per pass).  Same bits as the plain form.  Measured on 2^20 x 252
-// (profiles/r2_trajectory_tuning.txt): prices + counts 354 -> 345 us (6.12 TB/s); prices only 250 -> 251 us,
-// so the launcher uses it when counts / log2 prices are stored next to the prices.  (Conflict-free
-// staging -- TMA's 64-byte swizzle + one cp.async.bulk.tensor store per slab -- was also built and
-// measured: shared-memory bank conflicts 25.9 M -> 0.9 M, wavefronts 36.9 M -> 11.8 M, and NO gain, 255-266 us:
-// the conflicts were never the limiter; that variant is not shipped.)
+// (profiles/r2_trajectory_tuning.txt): prices 250 -> 238 us (4.44 TB/s), prices + counts 354 -> 344 us
+// (6.14 TB/s).  (Conflict-free staging -- TMA's 64-byte swizzle + one cp.async.bulk.tensor store per
+// slab -- was also built and measured: shared-memory bank conflicts 25.9 M -> 0.9 M, wavefronts 36.9 M ->
+// 11.8 M, and NO gain: the conflicts were never the limiter; that variant is not shipped.)
 template <int SPL, int LPR, int ROWS, int WARPS, bool COUNTS, bool LOGS, bool MULTI = false, bool ALIGNED = true,
           bool FAST = false>
 __global__ void __launch_bounds__(WARPS * 32)
