@@ -291,19 +291,27 @@ EuropeanParams european_params(const mcb_option_data *o, float K, float sigma, u
 
 struct WalkConsts {
     float l0, sc, dr, v, lB;
+    double l0d, scd, drd, lBd;   // the same in double (lBd = -inf without a barrier)
 };
 
 WalkConsts walk_consts(const mcb_option_data *o, double start)
 {
     WalkConsts w;
     const double r = o->r, sig = o->v, dt = o->step;
-    w.l0 = (float)std::log2(start);
-    w.sc = (float)(sig * std::sqrt(dt) * kLog2e * kSqrt2Ln2d);
-    w.dr = (float)((r - 0.5 * sig * sig) * dt * kLog2e);
+    w.l0d = std::log2(start);
+    w.scd = sig * std::sqrt(dt) * kLog2e * kSqrt2Ln2d;
+    w.drd = (r - 0.5 * sig * sig) * dt * kLog2e;
+    w.lBd = o->B > 0.0f ? std::log2((double)o->B) : -INFINITY;
+    w.l0 = (float)w.l0d;
+    w.sc = (float)w.scd;
+    w.dr = (float)w.drd;
     w.v = (float)(sig * std::sqrt(dt) * kLog2e);
-    w.lB = o->B > 0.0f ? (float)std::log2((double)o->B) : -INFINITY;
+    w.lB = (float)w.lBd;
     return w;
 }
+
+// Threshold table of the walk kernels in dynamic shared memory: n_steps floats rounded up to 4, when it fits.
+constexpr int kWalkTableMaxSteps = 8192;   // 32 KiB
 
 void segment_span(int rank, int world, uint64_t n_chunks, int *seg_lo, int *seg_hi, uint64_t *chunk_lo,
                   uint64_t *chunk_hi)
@@ -1193,15 +1201,27 @@ static int bullet_params(const mcb_option_data *opt, uint64_t n_paths_end, uint6
     // Sk == 0 means "start from S0" exactly as inc/trajectories.cuh:141
     const WalkConsts w = walk_consts(opt, Sk == 0.0f ? (double)opt->S0 : (double)Sk);
     WalkParams p{};
-    p.l0 = w.l0; p.sc = w.sc; p.dr = w.dr; p.lB = w.lB;
-    p.K = opt->K; p.P1 = opt->P1; p.P2 = opt->P2;
+    const bool barrier = std::isfinite(w.lBd);
     p.n_steps = opt->N_STEPS - Tk;
+    p.sc = w.sc;
+    // constants of the drift-free walk (pricing_kernels.cuh), formed in double from the SAME float sc / dr the
+    // trajectory kernels use, rounded once
+    p.acc0 = barrier ? (float)(-(w.lBd - w.l0d) / (double)w.sc) : 0.0f;
+    p.bq = barrier ? (float)((double)w.dr / (double)w.sc) : INFINITY;
+    p.l_end = (float)((barrier ? w.lBd : w.l0d) + (double)p.n_steps * (double)w.dr);
+    p.K = opt->K; p.P1 = opt->P1; p.P2 = opt->P2;
     p.count0 = Ik;
+    p.table = p.n_steps <= kWalkTableMaxSteps ? 1 : 0;
     p.n_paths = n_paths_end;
     p.first_chunk = first_chunk;
     p.keys = make_philox_keys(seed);
     *out = p;
     return MCB_OK;
+}
+
+static size_t walk_table_bytes(const WalkParams &p)
+{
+    return p.table ? (size_t)((p.n_steps + 3) & ~3) * sizeof(float) : 0;
 }
 
 static int bullet_segments_impl(mcb_engine *e, const mcb_option_data *opt, uint64_t n_paths, uint64_t seed, int Ik,
@@ -1227,8 +1247,8 @@ static int bullet_segments_impl(mcb_engine *e, const mcb_option_data *opt, uint6
     if (c_hi > c_lo) {
         {
             TimedScope timed(e, MCB_KERNEL_BULLET, st);
-            bullet_kernel<MCB_BULLET_PATHS_PER_SLOT><<<(unsigned)(c_hi - c_lo), kSlots, 0, st>>>(prm, e->partials.ptr,
-                                                                                                 nullptr, 0);
+            bullet_kernel<MCB_BULLET_PATHS_PER_SLOT><<<(unsigned)(c_hi - c_lo), kSlots, walk_table_bytes(prm), st>>>(
+                prm, e->partials.ptr, nullptr, 0);
         }
         e->launches++;
         CU(cudaGetLastError());
@@ -1503,8 +1523,12 @@ int mcb_nested_async(mcb_engine *e, const mcb_option_data *opt, uint64_t first_o
     if ((rc = trajectories_launch(e, opt, first_outer, n_outer, seed_outer, ws_prices, ws_counts, ws_logs, stream)))
         return rc;
     const WalkConsts w = walk_consts(opt, (double)opt->S0);
+    if (opt->N_STEPS > kWalkTableMaxSteps)
+        return fail(MCB_ERR_INVALID, "nested MC supports at most %d steps", kWalkTableMaxSteps);
     NestedParams prm{};
     prm.sc = w.sc; prm.dr = w.dr; prm.lB = w.lB;
+    prm.inv_sc = (float)(1.0 / (double)w.sc);
+    prm.bq = std::isfinite(w.lBd) ? (float)((double)w.dr / (double)w.sc) : INFINITY;
     prm.K = opt->K; prm.P1 = opt->P1; prm.P2 = opt->P2;
     prm.n_steps = opt->N_STEPS;
     prm.n_inner = opt->N_PATHS_INNER;
@@ -1521,7 +1545,8 @@ int mcb_nested_async(mcb_engine *e, const mcb_option_data *opt, uint64_t first_o
         uint64_t split = (want + n_outer - 1) / n_outer;
         if (split < 8) split = 8;
         if (split > (uint64_t)opt->N_STEPS) split = (uint64_t)opt->N_STEPS;
-        nested_kernel<<<dim3((unsigned)n_outer, (unsigned)split), kSlots, 0, st>>>(prm, ws_logs, ws_counts, d_F);
+        const size_t thr_bytes = (size_t)((opt->N_STEPS + 3) & ~3) * sizeof(float);
+        nested_kernel<<<dim3((unsigned)n_outer, (unsigned)split), kSlots, thr_bytes, st>>>(prm, ws_logs, ws_counts, d_F);
     }
     e->launches++;
     CU(cudaGetLastError());
@@ -1866,8 +1891,8 @@ int mcb_bullet_payoffs(mcb_engine *e, const mcb_option_data *opt, uint64_t first
     float *d = reinterpret_cast<float *>(e->scratch.ptr);
     WalkParams prm;
     if ((rc = bullet_params(opt, first_path + n_paths, seed, Ik, Sk, Tk, c_lo, &prm))) return rc;
-    bullet_kernel<MCB_BULLET_PATHS_PER_SLOT><<<(unsigned)(c_hi - c_lo), kSlots, 0, e->stream>>>(prm, e->partials.ptr, d,
-                                                                                                first_path);
+    bullet_kernel<MCB_BULLET_PATHS_PER_SLOT><<<(unsigned)(c_hi - c_lo), kSlots, walk_table_bytes(prm), e->stream>>>(
+        prm, e->partials.ptr, d, first_path);
     e->launches++;
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(payoffs, d, (size_t)n_paths * sizeof(float), cudaMemcpyDeviceToHost, e->stream));

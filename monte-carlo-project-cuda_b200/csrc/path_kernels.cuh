@@ -465,9 +465,10 @@ trajectory_slab_kernel(const __grid_constant__ PathParams prm, float *__restrict
 // RESTARTS from the point's state (the reference carries state over, inc/nmc.cuh:51-53).
 // ------------------------------------------------------------------------------------------
 struct NestedParams {
-    float sc, dr, lB, K;   // sc, dr: see WalkParams
+    float sc, inv_sc, bq, dr;   // sc, dr: see WalkParams; inv_sc = 1 / sc; bq = dr / sc (+inf without a barrier)
+    float lB, K;                // log2 B (-inf without a barrier)
     int P1, P2, n_steps, n_inner;
-    int discount_mode;     // MCB_DISCOUNT_*
+    int discount_mode;          // MCB_DISCOUNT_*
     float r, T, dt;
     uint64_t first_outer;
     PhiloxKeys keys_inner;
@@ -478,9 +479,12 @@ nested_kernel(const __grid_constant__ NestedParams prm, const float *__restrict_
               const int *__restrict__ counts, float *__restrict__ F)
 {
     __shared__ float scratch[2 * kWarps];
+    extern __shared__ __align__(16) float walk_thr[];   // thr[k] = -(k + 1) bq: the same for every point (see WalkParams)
     const uint64_t p = prm.first_outer + blockIdx.x;
     const int n_steps = prm.n_steps;
     const uint64_t row = (uint64_t)blockIdx.x * (uint64_t)n_steps;
+    const bool barrier = prm.lB > -INFINITY;
+    fill_walk_thresholds(walk_thr, n_steps, prm.bq);
 
     // gridDim.y CTAs share an outer trajectory, taking its points k = y, y + gridDim.y, ...: F[p,k]
     // depends on (p, k) only, and the interleaved split balances the work (a point costs
@@ -490,6 +494,9 @@ nested_kernel(const __grid_constant__ NestedParams prm, const float *__restrict_
         const float lo = __ldg(logs + row + k);
         const int co = __ldg(counts + row + k);
         const int remaining = n_steps - (k + 1);
+        // the inner walks of this point start at acc = -(log2 B - lo) / sc and end at l_end + sc * acc
+        const float acc0 = barrier ? (lo - prm.lB) * prm.inv_sc : 0.0f;
+        const float l_end = fmaf((float)remaining, prm.dr, barrier ? prm.lB : lo);
         float sum = 0.0f, sq = 0.0f;
         if (co <= prm.P2) {
             const uint64_t q = (p * (uint64_t)n_steps + (uint64_t)k) * (uint64_t)prm.n_inner;
@@ -502,30 +509,31 @@ nested_kernel(const __grid_constant__ NestedParams prm, const float *__restrict_
 #pragma unroll 1
             for (; jj + kSlots < prm.n_inner; jj += 2 * kSlots) {   // two inner paths interleaved
                 const uint64_t sa = q + (uint64_t)jj, sb = sa + kSlots;
-                float l[2] = {lo, lo};
+                float acc[2] = {acc0, acc0};
                 int c[2] = {co, co};
                 const uint32_t s_lo[2] = {(uint32_t)sa, (uint32_t)sb};
                 if (hi_uniform) {
                     const uint32_t s_hi[2] = {q_hi, q_hi};
-                    walk_paths<2>(l, c, s_lo, s_hi, remaining, prm.sc, prm.dr, prm.lB, prm.keys_inner);
+                    walk_paths<2>(acc, c, s_lo, s_hi, remaining, walk_thr, prm.bq, prm.keys_inner);
                 } else {
                     const uint32_t s_hi[2] = {(uint32_t)(sa >> 32), (uint32_t)(sb >> 32)};
-                    walk_paths<2>(l, c, s_lo, s_hi, remaining, prm.sc, prm.dr, prm.lB, prm.keys_inner);
+                    walk_paths<2>(acc, c, s_lo, s_hi, remaining, walk_thr, prm.bq, prm.keys_inner);
                 }
 #pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    const float pay = (c[k] >= prm.P1 && c[k] <= prm.P2) ? fmaxf(mufu_ex2(l[k]) - prm.K, 0.0f) : 0.0f;
+                for (int i = 0; i < 2; ++i) {
+                    const float pay = (c[i] >= prm.P1 && c[i] <= prm.P2)
+                                          ? fmaxf(mufu_ex2(fmaf(prm.sc, acc[i], l_end)) - prm.K, 0.0f) : 0.0f;
                     sum = sum + pay;
                     sq = fmaf(pay, pay, sq);
                 }
             }
             if (jj < prm.n_inner) {
                 const uint64_t sub = q + (uint64_t)jj;
-                float l = lo;
+                float acc = acc0;
                 int c = co;
-                walk_path(l, c, (uint32_t)sub, (uint32_t)(sub >> 32), remaining, prm.sc, prm.dr, prm.lB,
-                          prm.keys_inner);
-                const float pay = (c >= prm.P1 && c <= prm.P2) ? fmaxf(mufu_ex2(l) - prm.K, 0.0f) : 0.0f;
+                walk_path(acc, c, (uint32_t)sub, (uint32_t)(sub >> 32), remaining, walk_thr, prm.bq, prm.keys_inner);
+                const float pay = (c >= prm.P1 && c <= prm.P2) ? fmaxf(mufu_ex2(fmaf(prm.sc, acc, l_end)) - prm.K, 0.0f)
+                                                                : 0.0f;
                 sum = sum + pay;
                 sq = fmaf(pay, pay, sq);
             }

@@ -149,6 +149,21 @@ __device__ __forceinline__ void increments4(const Words4 &w, float scale, float 
     d[3] = fmaf(t1, mufu_cos(v1), shift);
 }
 
+// The four UNIT normals of a Philox block as (radius, trig) factors, left unmultiplied: normal j is
+// r[j / 2] * g[j] with r the unscaled Box-Muller radius sqrt(-log2 u) and g = sin, cos, sin, cos.  The
+// multi-step walks feed them straight into the accumulating FFMA (acc = fma(r, g, acc)): no scaling
+// multiply and no separate add per step.
+__device__ __forceinline__ void unit_factors4(const Words4 &w, float r[2], float g[4])
+{
+    r[0] = bm_radius_unscaled(w.x);
+    r[1] = bm_radius_unscaled(w.z);
+    const float v0 = bm_angle(w.y), v1 = bm_angle(w.w);
+    g[0] = mufu_sin(v0);
+    g[1] = mufu_cos(v0);
+    g[2] = mufu_sin(v1);
+    g[3] = mufu_cos(v1);
+}
+
 // ---- packed FP32x2 arithmetic (sm_100: FFMA2 / FADD2 / FMUL2) -------------------------------------
 // One instruction works on TWO floats held in an even-aligned register pair.  The FMA pipes do
 // not get faster (128 lanes per SM either way), but the hot kernels here are bound by ISSUE SLOTS

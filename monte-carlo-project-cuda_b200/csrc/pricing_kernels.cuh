@@ -221,82 +221,96 @@ sweep_kernel(const __grid_constant__ SweepParams prm, const float4 *__restrict__
 }
 
 // ------------------------------------------------------------------------------------------
-// Multi-step GBM walk in log2 space, fused drift + diffusion: the FFMA that scales the
-// Box-Muller radius by the trig value anyway also applies the volatility and adds the drift
-// (increments4), so a step is ONE FADD, l += d; the barrier test is l < log2 B; one MUFU.EX2 at
-// the end.  One Philox block feeds four steps.
+// Multi-step GBM walk in log2 space with the drift and the volatility taken OUT of the loop.
+// After k + 1 steps   log2 S = l0 + (k + 1) dr + sc * sum_{i <= k} z_i   (z_i: unit normals / sqrt(2 ln 2),
+// sc = sigma sqrt(dt) log2 e sqrt(2 ln 2), dr = (r - sigma^2/2) dt log2 e), so with
+//     acc_k = sum_{i <= k} z_i - A,   A = (log2 B - l0) / sc,   Bq = dr / sc
+// the barrier test  log2 S < log2 B  is  acc_k < -(k + 1) Bq:  the right-hand sides are the same for
+// every path (a table of n_steps floats in shared memory, one LDS.128 per Philox block), and a step is
+//     acc = fma(radius, trig, acc);  count += acc < thr[k]
+// -- ONE FFMA per step, where the scaled-increment form needs a multiply, an FFMA and an add (every FP32
+// instruction costs this loop ~1 clk of the pipe the Philox multiplies saturate, profiles/r2_pipe_microbench.txt).
+// At the end  log2 S_T = l_end + sc * acc  with l_end = log2 B + n dr  (l0 + n dr and acc_0 = 0, thr = -inf
+// when there is no barrier).  One Philox block feeds four steps; one MUFU.EX2 per path.
 // ------------------------------------------------------------------------------------------
 struct WalkParams {
-    float l0;      // log2 of the start price
+    float acc0;    // -(log2 B - l0) / sc   (0 without a barrier)
     float sc;      // sigma sqrt(dt) log2(e) sqrt(2 ln 2): scale of the unscaled Box-Muller radius (> 0)
-    float dr;      // (r - sigma^2/2) dt log2(e): drift per step in log2 units
-    float lB;      // log2 B  (-inf when B <= 0: the barrier is never hit)
+    float bq;      // dr / sc: the barrier thresholds are -(k + 1) bq   (+inf without a barrier)
+    float l_end;   // log2 B + n_steps dr   (l0 + n_steps dr without a barrier)
     float K;
     int P1, P2;
     int n_steps;   // steps to walk
     int count0;    // initial barrier count (Ik)
-    uint32_t pad;
+    int table;     // 1: the launch carries n_steps (rounded up to 4) floats of dynamic shared memory for thr[]
     uint64_t n_paths;
     uint64_t first_chunk;
     PhiloxKeys keys;
 };
 
-// Walk `n_steps` steps of N independent streams (keys, subsequence[k]) from (l[k], count[k]);
-// normal i of a stream drives step i.  N > 1 interleaves the integer (Philox) chains of several
-// paths in one thread: same arithmetic per path, more instruction-level parallelism.
+// thr[k] = -(k + 1) bq for the steps [0, n_steps), padded to a multiple of 4; all threads of the CTA call it
+__device__ __forceinline__ void fill_walk_thresholds(float *thr, int n_steps, float bq)
+{
+    const int n4 = (n_steps + 3) & ~3;
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) thr[i] = -(float)(i + 1) * bq;
+    __syncthreads();
+}
+
+// Walk `n_steps` steps of N independent streams (keys, subsequence[k]) from (acc[k], count[k]);
+// normal i of a stream drives step i.  thr: the threshold table (nullptr: the four thresholds of a block
+// are computed on the spot, for walks too long for shared memory).  N > 1 interleaves the integer
+// (Philox) chains of several paths in one thread: same arithmetic per path, more instruction-level
+// parallelism.
 template <int N>
-__device__ __forceinline__ void walk_paths(float (&l)[N], int (&count)[N], const uint32_t (&s_lo)[N],
-                                           const uint32_t (&s_hi)[N], int n_steps, float sc, float dr, float lB,
+__device__ __forceinline__ void walk_paths(float (&acc)[N], int (&count)[N], const uint32_t (&s_lo)[N],
+                                           const uint32_t (&s_hi)[N], int n_steps, const float *thr, float bq,
                                            const PhiloxKeys &keys)
 {
-    const int full = n_steps >> 2;
-#pragma unroll 1
-    for (int b = 0; b < full; ++b) {
-        float d[N][4];
+    auto one_block = [&](int b, int steps /* 4, or 1..3 in a ragged last block */) {
+        float4 th;
+        if (thr) {
+            th = *reinterpret_cast<const float4 *>(thr + 4 * b);
+        } else {
+            th.x = -(float)(4 * b + 1) * bq;
+            th.y = -(float)(4 * b + 2) * bq;
+            th.z = -(float)(4 * b + 3) * bq;
+            th.w = -(float)(4 * b + 4) * bq;
+        }
+        float r[N][2], g[N][4];
 #pragma unroll
-        for (int k = 0; k < N; ++k) increments4(philox4x32_10((uint32_t)b, 0u, s_lo[k], s_hi[k], keys), sc, dr, d[k]);
+        for (int k = 0; k < N; ++k) unit_factors4(philox4x32_10((uint32_t)b, 0u, s_lo[k], s_hi[k], keys), r[k], g[k]);
+        const float t[4] = {th.x, th.y, th.z, th.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-#pragma unroll
-            for (int k = 0; k < N; ++k) {
-                l[k] = l[k] + d[k][j];
-                count[k] += (l[k] < lB) ? 1 : 0;
-            }
-        }
-    }
-    const int tail = n_steps & 3;
-    if (tail) {
-        float d[N][4];
-#pragma unroll
-        for (int k = 0; k < N; ++k)
-            increments4(philox4x32_10((uint32_t)full, 0u, s_lo[k], s_hi[k], keys), sc, dr, d[k]);
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            if (j < tail) {
+            if (j < steps) {
 #pragma unroll
                 for (int k = 0; k < N; ++k) {
-                    l[k] = l[k] + d[k][j];
-                    count[k] += (l[k] < lB) ? 1 : 0;
+                    acc[k] = fmaf(r[k][j >> 1], g[k][j], acc[k]);
+                    count[k] += (acc[k] < t[j]) ? 1 : 0;
                 }
             }
         }
-    }
+    };
+    const int full = n_steps >> 2;
+#pragma unroll 1
+    for (int b = 0; b < full; ++b) one_block(b, 4);
+    if (n_steps & 3) one_block(full, n_steps & 3);
 }
 
-__device__ __forceinline__ void walk_path(float &l, int &count, uint32_t s_lo, uint32_t s_hi, int n_steps,
-                                          float sc, float dr, float lB, const PhiloxKeys &keys)
+__device__ __forceinline__ void walk_path(float &acc, int &count, uint32_t s_lo, uint32_t s_hi, int n_steps,
+                                          const float *thr, float bq, const PhiloxKeys &keys)
 {
-    float l1[1] = {l};
+    float a1[1] = {acc};
     int c1[1] = {count};
     const uint32_t lo1[1] = {s_lo}, hi1[1] = {s_hi};
-    walk_paths<1>(l1, c1, lo1, hi1, n_steps, sc, dr, lB, keys);
-    l = l1[0];
+    walk_paths<1>(a1, c1, lo1, hi1, n_steps, thr, bq, keys);
+    acc = a1[0];
     count = c1[0];
 }
 
-__device__ __forceinline__ float bullet_payoff_from(float l, int count, const WalkParams &prm)
+__device__ __forceinline__ float bullet_payoff_from(float acc, int count, const WalkParams &prm)
 {
-    const float pay = fmaxf(mufu_ex2(l) - prm.K, 0.0f);
+    const float pay = fmaxf(mufu_ex2(fmaf(prm.sc, acc, prm.l_end)) - prm.K, 0.0f);
     return (count >= prm.P1 && count <= prm.P2) ? pay : 0.0f;
 }
 
@@ -306,6 +320,9 @@ bullet_kernel(const __grid_constant__ WalkParams prm, float2 *__restrict__ parti
               float *__restrict__ payoffs, uint64_t payoffs_first_path)
 {
     __shared__ float scratch[2 * kWarps];
+    extern __shared__ __align__(16) float walk_thr[];
+    const float *thr = prm.table ? walk_thr : nullptr;
+    if (prm.table) fill_walk_thresholds(walk_thr, prm.n_steps, prm.bq);
     const uint64_t chunk = prm.first_chunk + blockIdx.x;
     const uint64_t base = chunk * (uint64_t)(kSlots * PPS);
     const uint64_t left = prm.n_paths - base;
@@ -317,17 +334,17 @@ bullet_kernel(const __grid_constant__ WalkParams prm, float2 *__restrict__ parti
         if ((uint64_t)local + kSlots < left) {
             // both paths of the pair exist: walk them interleaved, accumulate in slot order
             const uint64_t pa = base + local, pb = pa + kSlots;
-            float l[2] = {prm.l0, prm.l0};
+            float acc[2] = {prm.acc0, prm.acc0};
             int count[2] = {prm.count0, prm.count0};
             // a chunk (1024 consecutive, 1024-aligned paths) never straddles a multiple of 2^32: the high
             // stream word is the CTA-uniform high word of `base`, so the round-1 product it feeds
             // (M1 * (hi(M0 * block) ^ p_hi ^ k1[0])) lives on the uniform datapath, off the multiplier pipe
             const uint32_t p_hi = (uint32_t)(base >> 32);
             const uint32_t lo[2] = {(uint32_t)pa, (uint32_t)pb}, hi[2] = {p_hi, p_hi};
-            walk_paths<2>(l, count, lo, hi, prm.n_steps, prm.sc, prm.dr, prm.lB, prm.keys);
+            walk_paths<2>(acc, count, lo, hi, prm.n_steps, thr, prm.bq, prm.keys);
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
-                const float pay = bullet_payoff_from(l[k], count[k], prm);
+                const float pay = bullet_payoff_from(acc[k], count[k], prm);
                 sum = sum + pay;
                 sq = fmaf(pay, pay, sq);
                 const uint64_t p = k ? pb : pa;
@@ -335,10 +352,10 @@ bullet_kernel(const __grid_constant__ WalkParams prm, float2 *__restrict__ parti
             }
         } else if ((uint64_t)local < left) {
             const uint64_t p = base + local;
-            float l = prm.l0;
+            float acc = prm.acc0;
             int count = prm.count0;
-            walk_path(l, count, (uint32_t)p, (uint32_t)(p >> 32), prm.n_steps, prm.sc, prm.dr, prm.lB, prm.keys);
-            const float pay = bullet_payoff_from(l, count, prm);
+            walk_path(acc, count, (uint32_t)p, (uint32_t)(p >> 32), prm.n_steps, thr, prm.bq, prm.keys);
+            const float pay = bullet_payoff_from(acc, count, prm);
             sum = sum + pay;
             sq = fmaf(pay, pay, sq);
             if (payoffs && p >= payoffs_first_path) payoffs[p - payoffs_first_path] = pay;
