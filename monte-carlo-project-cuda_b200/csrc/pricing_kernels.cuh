@@ -128,7 +128,9 @@ __global__ void __launch_bounds__(kSlots)
 sweep_kernel(const __grid_constant__ SweepParams prm, const float4 *__restrict__ sets /* (c0, c1, K, -) */,
              float2 *__restrict__ partials)
 {
-    __shared__ float scratch[2 * kSweepTile][kWarps];
+    __shared__ float scratch[2][2 * kSweepTile][kWarps];   // double-buffered: one barrier per tile
+    int tile_parity = 0;
+    static_assert(kSweepTile == 4 && kWarps == 8, "the tile fold below is written for 8 values x 8 warps");
     const uint64_t chunk = prm.first_chunk + blockIdx.x;
     const uint64_t base = chunk * (uint64_t)(kSlots * PPS);
     const uint32_t p_hi = (uint32_t)(base >> 32);
@@ -187,36 +189,56 @@ sweep_kernel(const __grid_constant__ SweepParams prm, const float4 *__restrict__
             if (!have0) sum[k] = sq[k] = 0.0f;
             if (!have1) sum[k + 1] = sq[k + 1] = 0.0f;
         }
-        // same tree as block_fold2, kSweepTile parameter sets at a time
+        // block_fold2's tree for the tile's eight values (sum, sumsq of four sets) at once.  A plain
+        // warp_fold per value costs 8 x 5 shuffles, and shuffles queue in the same MIO pipe as the MUFU
+        // instructions this kernel is bound by (ncu: mio_throttle is its top stall).  Here the lanes split the
+        // eight values between them as they fold -- at offset 16 each lane keeps four values and receives its
+        // partner's four, at offset 8 two, at offset 4 one -- so the whole warp stage is 4 + 2 + 1 + 1 + 1 = 9
+        // shuffles.  Every addition pairs exactly the operands warp_fold's lane 0 pairs (slot p with slot
+        // p + offset; IEEE addition commutes), so the bits are unchanged; lane 4k ends up with value k.
+        const float v8[2 * kSweepTile] = {sum[0], sq[0], sum[1], sq[1], sum[2], sq[2], sum[3], sq[3]};
+        float k4[4], k2[2], k1;
+        {
+            const bool up = (lane & 16) != 0;
 #pragma unroll
-        for (int k = 0; k < kSweepTile; ++k) {
-            sum[k] = warp_fold(sum[k]);
-            sq[k] = warp_fold(sq[k]);
-        }
-        if (lane == 0) {
-#pragma unroll
-            for (int k = 0; k < kSweepTile; ++k) {
-                scratch[2 * k][warp] = sum[k];
-                scratch[2 * k + 1][warp] = sq[k];
+            for (int j = 0; j < 4; ++j) {
+                const float keep = up ? v8[4 + j] : v8[j], send = up ? v8[j] : v8[4 + j];
+                k4[j] = keep + __shfl_xor_sync(kFullMask, send, 16);
             }
         }
+        {
+            const bool up = (lane & 8) != 0;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const float keep = up ? k4[2 + j] : k4[j], send = up ? k4[j] : k4[2 + j];
+                k2[j] = keep + __shfl_xor_sync(kFullMask, send, 8);
+            }
+        }
+        {
+            const bool up = (lane & 4) != 0;
+            const float keep = up ? k2[1] : k2[0], send = up ? k2[0] : k2[1];
+            k1 = keep + __shfl_xor_sync(kFullMask, send, 4);
+        }
+        k1 = k1 + __shfl_xor_sync(kFullMask, k1, 2);
+        k1 = k1 + __shfl_xor_sync(kFullMask, k1, 1);
+        float(*buf)[kWarps] = scratch[tile_parity];
+        if ((lane & 3) == 0) buf[lane >> 2][warp] = k1;          // value index = lane / 4
         __syncthreads();
+        // the 8 -> 1 step over the warps, four values at a time on eight lanes each; the other warps go on to
+        // the next tile (its scratch is the other buffer, so one barrier per tile is enough)
         if (warp == 0) {
 #pragma unroll
-            for (int k = 0; k < 2 * kSweepTile; ++k) {
-                float x = lane < kWarps ? scratch[k][lane] : 0.0f;
+            for (int h = 0; h < 2; ++h) {
+                float x = buf[4 * h + (lane >> 3)][lane & 7];
 #pragma unroll
-                for (int off = kWarps / 2; off > 0; off >>= 1) x = x + __shfl_down_sync(kFullMask, x, off);
-                if (k & 1) sq[k >> 1] = x; else sum[k >> 1] = x;
-            }
-            if (lane == 0) {
-#pragma unroll
-                for (int k = 0; k < kSweepTile; ++k)
-                    if (s0 + k < set_end)
-                        partials[(uint64_t)(s0 + k) * prm.stride + blockIdx.x] = make_float2(sum[k], sq[k]);
+                for (int off = kWarps / 2; off > 0; off >>= 1) x = x + __shfl_down_sync(kFullMask, x, off, 8);
+                const float q = __shfl_down_sync(kFullMask, x, 8);           // the sum of squares sits 8 lanes up
+                const int set = s0 + 2 * h + (lane >> 4);
+                if ((lane & 15) == 0 && set < set_end)
+                    partials[(uint64_t)set * prm.stride + blockIdx.x] = make_float2(x, q);
             }
         }
-        __syncthreads();
+        tile_parity ^= 1;
     }
 }
 
