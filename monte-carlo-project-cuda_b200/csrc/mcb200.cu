@@ -100,11 +100,13 @@ struct ShardWorker {
     std::atomic<unsigned long long> posted{0}, done{0};
     std::function<int()> job;
     int rc = 0;
+    int device = 0;
     std::string message;
     bool quit = false;
 
     void loop()
     {
+        cudaSetDevice(device);   // this thread only ever launches on its shard's device
         unsigned long long seen = 0;
         for (;;) {
             int spins = 0;
@@ -598,7 +600,10 @@ int mcb_engine_create_multi(const int *devices, int n_devices, mcb_engine **out)
             for (size_t r = 0; r < shards.size(); ++r) s->peers.box[r] = shards[r]->mailbox;
             if (i) {
                 s->worker = new (std::nothrow) ShardWorker();
-                if (s->worker) s->worker->thread = std::thread([w = s->worker] { w->loop(); });
+                if (s->worker) {
+                    s->worker->device = s->device;
+                    s->worker->thread = std::thread([w = s->worker] { w->loop(); });
+                }
             }
         }
         L->shards = shards;
