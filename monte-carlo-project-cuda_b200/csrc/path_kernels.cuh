@@ -474,7 +474,7 @@ struct NestedParams {
     PhiloxKeys keys_inner;
 };
 
-__global__ void __launch_bounds__(kSlots)
+__global__ void __launch_bounds__(kSlots, 5)   // <= 48 registers: 40 warps per SM
 nested_kernel(const __grid_constant__ NestedParams prm, const float *__restrict__ logs,
               const int *__restrict__ counts, float *__restrict__ F)
 {

@@ -337,7 +337,7 @@ __device__ __forceinline__ float bullet_payoff_from(float acc, int count, const 
 }
 
 template <int PPS>
-__global__ void __launch_bounds__(kSlots)
+__global__ void __launch_bounds__(kSlots, 6)   // 40 registers: 48 warps per SM (the loop needs 42 without the cap)
 bullet_kernel(const __grid_constant__ WalkParams prm, float2 *__restrict__ partials,
               float *__restrict__ payoffs, uint64_t payoffs_first_path)
 {
