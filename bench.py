@@ -69,8 +69,8 @@ def bs_call(S0, K, T, r, v):
 
 def ncu_traffic(kernel):
     """DRAM bytes per launch (read + write) of `kernel` from the committed ncu --set full capture
-    (profiles/r1_ncu_traffic.json, written by tools/ncu_traffic.py); None when not captured."""
-    path = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+    (profiles/r2_ncu_traffic.json, written by tools/ncu_traffic.py); None when not captured."""
+    path = os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")
     try:
         with open(path) as f:
             return json.load(f)[kernel]["traffic"]
@@ -468,8 +468,9 @@ def run_b200(args):
         sms = eng.device_info().sm_count
         peak = sms * ISSUE_PER_CLK_PER_SM * sm_max_mhz * 1e6 / 1e12
         line["roofline"] = {
-            "bound": "issue", "kernel": "european_job_kernel", "achieved": achieved, "peak": peak, "unit": "Tinstr/s",
-            "frac": achieved / peak, "traffic": ncu_traffic("european_job_kernel"),
+            "bound": "issue", "kernel": "european_kernel (shards of >= 2^26 paths; european_job_kernel below)",
+            "achieved": achieved, "peak": peak, "unit": "Tinstr/s",
+            "frac": achieved / peak, "traffic": ncu_traffic("european_kernel"),
             "traffic_note": "DRAM bytes per launch from ncu --set full (profiles/*_ncu_traffic.json); the kernel "
                             "reads no global memory, algorithmic bytes = 512 KiB of chunk partials (stay in L2)",
             "per_unit": f"{INSTR_PER_EUROPEAN_PATH} thread-instr/path (SURVEY 8(d))",

@@ -198,3 +198,45 @@ def test_reference_hello_cu_on_all_shards(pkg):
     one = prices(None)
     assert len(one) >= 5
     assert prices("0,0,0") == one
+
+
+def _silent_peer(conn):
+    """A second process that exports a mailbox and then never submits a job."""
+    import __graft_entry__ as entry
+    pkg = entry.load_package()
+    eng = pkg.Engine(0)
+    conn.send((eng.peer_mailbox_create(), eng.peer_epoch()))
+    conn.recv()          # the parent is done
+    eng.close()
+
+
+def test_a_missing_peer_poisons_the_result_instead_of_inventing_one(pkg, engine):
+    """a peer that never delivers must not yield a plausible price.  Rank 0 of a two-rank process group
+    (CUDA-IPC mailboxes) submits a job; rank 1 never does.  The final pass gives up at the %globaltimer deadline,
+    writes NaN / n_paths = 0, collect returns MCB_ERR_TIMEOUT, and the engine prices normally again once it is back
+    in a group of one.  (Safe on one GPU: the only kernel that waits is bounded and nothing else needs to run.)"""
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    parent, child = ctx.Pipe()
+    proc = ctx.Process(target=_silent_peer, args=(child,))
+    proc.start()
+    eng = pkg.Engine(0)
+    try:
+        peer_handle, peer_epoch = parent.recv()
+        mine = eng.peer_mailbox_create()
+        eng.peer_mailbox_connect(0, 2, [mine, peer_handle], max(eng.peer_epoch(), peer_epoch))
+        eng.set_wait_timeout_ms(50)
+        n = 100 * pkg.EUROPEAN_CHUNK + 7
+        ticket = eng.european_submit(pkg.option(), n, 1234, pkg.CALL)
+        with pytest.raises(pkg.McbError) as ei:
+            eng.european_collect(ticket)
+        assert ei.value.status == pkg.ERR_TIMEOUT
+        assert eng.peer_timeouts() >= 1
+        # back to a group of one: same engine, same bits as ever
+        eng.peer_mailbox_connect(0, 1, [mine], eng.peer_epoch())
+        got = eng.price_european(pkg.option(), n, 1234, pkg.CALL)
+        assert _bits(got) == _bits(engine.price_european(pkg.option(), n, 1234, pkg.CALL))
+    finally:
+        parent.send("done")
+        proc.join(timeout=60)
+        eng.close()

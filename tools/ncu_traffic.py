@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Extract per-launch DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) of the captured kernels
-into profiles/r1_ncu_traffic.json, which bench.py quotes as roofline.traffic.
-    python tools/ncu_traffic.py gpurun_out/prof_european_r1_final.ncu-rep gpurun_out/prof_trajectory_r1_final.ncu-rep"""
+into profiles/r2_ncu_traffic.json, which bench.py quotes as roofline.traffic.
+    python tools/ncu_traffic.py gpurun_out/prof_european_r2.ncu-rep gpurun_out/prof_trajectory_r2.ncu-rep"""
 import csv, io, json, subprocess, sys
 UNIT = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 out = {}
@@ -17,5 +17,5 @@ for rep in sys.argv[1:]:
         out[name] = {"dram_bytes_read": rd, "dram_bytes_write": wr, "traffic": rd + wr,
                      "gpu_time_us": float(d["gpu__time_duration.sum"]) * {"us": 1, "ms": 1e3, "ns": 1e-3}[u["gpu__time_duration.sum"]],
                      "grid": d["Grid Size"], "block": d["Block Size"], "source": rep.split("/")[-1]}
-json.dump(out, open("profiles/r1_ncu_traffic.json", "w"), indent=1)
+json.dump(out, open("profiles/r2_ncu_traffic.json", "w"), indent=1)
 print(json.dumps(out, indent=1))
