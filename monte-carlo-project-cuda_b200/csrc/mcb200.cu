@@ -417,11 +417,12 @@ void launch_trajectory(const PathParams &prm_in, uint64_t n_paths, bool vec, boo
     constexpr int kRowsPerWarp = 32 / LPR;
     constexpr int kSlabWarps = 4;
     const PathParams &prm = prm_in;
-    // rows longer than one pass: one row group per slab, the whole rows staged -- while the staging
-    // leaves enough CTAs per SM (measured on 2^20 rows: prices only 4.07 TB/s at 1024 steps / 32 KB,
-    // 3.67 at 1536 / 48 KB, then the general kernel's 3.5 TB/s wins; with counts the general
-    // kernel's direct stores are slow enough that staging pays up to 72 KB); longer or unaligned
-    // rows take the general kernel
+    // rows longer than one pass: one row group per slab with the whole rows staged while that leaves enough CTAs
+    // per SM (<= 40 KB per CTA), pass-by-pass staging beyond (trajectory_long_kernel).  Measured on 2^18-2^20
+    // rows (tools/traj_long_bench.py, profiles/r2_trajectory_tuning.txt), whole-row / pass-wise / general kernel:
+    // prices 512 steps 4.15 / 3.62, 1024: 4.04 / 3.75, 1536: 3.63 / 3.72 / 3.63, 2048: - / 3.75 / 3.38, 4096: - / 3.78 /
+    // 3.37 TB/s; prices + counts 512: 5.92 / 5.31, 1024: 4.58 / 5.23, 1536: - / 5.31 / 2.76, 4096: - / 5.29 / 2.75 TB/s.
+    // Unaligned rows longer than a pass take the general kernel.
     const int n_arrays = 1 + (d_counts ? 1 : 0) + (d_logs ? 1 : 0);
     const size_t multi_smem = (size_t)kSlabWarps * n_arrays * kRowsPerWarp * (size_t)prm.n_steps * sizeof(float);
 #define MCB_SLAB_W(ROWS, CNT, LOG, MULTI, ALIGNED, FAST, WARPS)                                               \
@@ -436,7 +437,8 @@ void launch_trajectory(const PathParams &prm_in, uint64_t n_paths, bool vec, boo
     } while (0)
 #define MCB_SLAB(ROWS, CNT, LOG, MULTI, ALIGNED) MCB_SLAB_W(ROWS, CNT, LOG, MULTI, ALIGNED, false, kSlabWarps)
     // (only the largest layout is ever asked for rows longer than its pass)
-    if (SPL * LPR == 256 && vec && prm.n_steps > SPL * LPR && multi_smem <= (n_arrays == 1 ? 48 : 72) * 1024) {
+    const int long_mode = env_int("MCB_TRAJ_LONG", 1);   // tools/: 0 general kernel, 2 pass-wise staging for every long row
+    if (SPL * LPR == 256 && vec && prm.n_steps > SPL * LPR && multi_smem <= 40 * 1024 && long_mode != 2) {
         if constexpr (SPL * LPR == 256) {
             if (d_counts && d_logs) MCB_SLAB(kRowsPerWarp, true, true, true, true);
             else if (d_counts) MCB_SLAB(kRowsPerWarp, true, false, true, true);
@@ -466,6 +468,25 @@ void launch_trajectory(const PathParams &prm_in, uint64_t n_paths, bool vec, boo
         else MCB_SLAB(8, false, false, false, false);
 #undef MCB_SLAB
 #undef MCB_SLAB_W
+    } else if (SPL * LPR == 256 && vec && prm.n_steps > SPL * LPR && long_mode != 0) {
+        // rows too long to stage whole: pass-by-pass staging, two 1 KiB bulk stores per pass and array
+        if constexpr (SPL * LPR == 256) {
+            constexpr int kLongWarps = 4;
+            const uint64_t pairs = (n_paths + 1) / 2;
+            const unsigned ctas = (unsigned)((pairs + kLongWarps - 1) / kLongWarps);
+            const size_t smem = (size_t)kLongWarps * 2 * n_arrays * 2 * 256 * sizeof(float);
+#define MCB_LONG(CNT, LOG)                                                                                    \
+            do {                                                                                              \
+                auto kern = trajectory_long_kernel<CNT, LOG, kLongWarps>;                                     \
+                if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+                kern<<<ctas, kLongWarps * 32, smem, st>>>(prm, d_prices, d_counts, d_logs);                   \
+            } while (0)
+            if (d_counts && d_logs) MCB_LONG(true, true);
+            else if (d_counts) MCB_LONG(true, false);
+            else if (d_logs) MCB_LONG(false, true);
+            else MCB_LONG(false, false);
+#undef MCB_LONG
+        }
     } else {
         const uint64_t rows_per_cta = (uint64_t)kPathWarps * kPathsPerWarp * kRowsPerWarp;
         const unsigned g = (unsigned)((n_paths + rows_per_cta - 1) / rows_per_cta), b = kPathWarps * 32;

@@ -455,6 +455,101 @@ trajectory_slab_kernel(const __grid_constant__ PathParams prm, float *__restrict
 }
 
 // ------------------------------------------------------------------------------------------
+// Long rows (more steps than a slab can stage whole; 16-byte aligned): the same 16 x 16 passes, staged PASS
+// BY PASS.  A pass of a row pair is two contiguous 1 KiB pieces of the output per array; the lanes park them
+// in one of two shared-memory buffers and an elected lane hands each piece to the TMA engine
+// (cp.async.bulk), so the next pass computes while the previous one drains -- instead of 64-byte
+// per-lane STG.128 straight from registers (half-filled sectors whenever a row does not start on a sector:
+// the general kernel reaches 3.5 TB/s with prices only and 1.4 TB/s with counts at 2048+ steps).
+// Same row_words / row_finish as every other trajectory kernel: same bits.
+// Dynamic shared memory: WARPS * 2 buffers * arrays * 2 rows * 256 floats.
+// ------------------------------------------------------------------------------------------
+template <bool COUNTS, bool LOGS, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+trajectory_long_kernel(const __grid_constant__ PathParams prm, float *__restrict__ prices, int *__restrict__ counts,
+                       float *__restrict__ logs)
+{
+    constexpr int SPL = 16, LPR = 16, kPass = SPL * LPR, kArrays = 1 + (COUNTS ? 1 : 0) + (LOGS ? 1 : 0);
+    constexpr int kBuf = kArrays * 2 * kPass;             // floats of one buffer: [array][row of the pair][256]
+    extern __shared__ __align__(128) float stage[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sub = lane / LPR, ln = lane % LPR;
+    const int n_steps = prm.n_steps;
+    const uint32_t n_rows = (uint32_t)prm.n_paths;
+    const uint32_t n_pairs = (n_rows + 1) / 2;
+    const int lane_step = SPL * ln;
+    float *my = stage + (size_t)warp * 2 * kBuf;
+    unsigned pass_no = 0;                                   // alternates the two buffers across passes AND row pairs
+
+#pragma unroll 1
+    for (uint32_t pair = blockIdx.x * WARPS + warp; pair < n_pairs; pair += gridDim.x * WARPS) {
+        const uint32_t row = 2 * pair + (uint32_t)sub;      // a row past n_rows is computed and not copied
+        const uint64_t p = prm.first_path + row;
+        float carry_l = prm.l0;
+        int carry_c = 0;
+#pragma unroll 1
+        for (int step0 = 0; step0 < n_steps; step0 += kPass, ++pass_no) {
+            const int my_step = step0 + lane_step;
+            const bool active = my_step < n_steps;
+            float a[SPL];
+            const float base = row_finish<SPL, LPR>(prm, row_words<SPL>(prm, (uint32_t)p, (uint32_t)(p >> 32), my_step),
+                                                    active, carry_l, a);
+#pragma unroll
+            for (int j = 0; j < SPL; ++j) a[j] = base + a[j];
+            int cbase = carry_c;
+            if (COUNTS) {
+                int run = 0;
+#pragma unroll
+                for (int j = 0; j < SPL; ++j) run += (a[j] < prm.lB && my_step + j < n_steps) ? 1 : 0;
+                cbase += group_exclusive_scan<LPR>(run);
+                carry_c = __shfl_sync(kFullMask, cbase + run, LPR - 1, LPR);
+            }
+            float *buf = my + (pass_no & 1u) * kBuf;
+            if (lane == 0) bulk_wait_read<1>();             // the copies of two passes ago have read this buffer
+            __syncwarp();
+            float *dst = buf + sub * kPass + lane_step;
+#pragma unroll
+            for (int b = 0; b < SPL / 4; ++b) {
+                if (my_step + 4 * b < n_steps) {            // n_steps % 4 == 0: whole float4s are in range
+                    float s4[4];
+                    int c[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        s4[j] = mufu_ex2(a[4 * b + j]);
+                        if (COUNTS) {
+                            cbase += (a[4 * b + j] < prm.lB) ? 1 : 0;
+                            c[j] = cbase;
+                        }
+                    }
+                    *reinterpret_cast<float4 *>(dst + 4 * b) = make_float4(s4[0], s4[1], s4[2], s4[3]);
+                    if (COUNTS) *reinterpret_cast<int4 *>(dst + 2 * kPass + 4 * b) = make_int4(c[0], c[1], c[2], c[3]);
+                    if (LOGS)
+                        *reinterpret_cast<float4 *>(dst + (COUNTS ? 4 : 2) * kPass + 4 * b) =
+                            make_float4(a[4 * b], a[4 * b + 1], a[4 * b + 2], a[4 * b + 3]);
+                }
+            }
+            fence_async_smem();                             // generic-proxy STS -> visible to the async proxy (TMA)
+            __syncwarp();
+            if (lane == 0) {
+                const uint32_t bytes = (uint32_t)min(kPass, n_steps - step0) * 4u;
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    const uint32_t r = 2 * pair + (uint32_t)s;
+                    if (r < n_rows) {
+                        const uint64_t off = (uint64_t)r * (uint32_t)n_steps + (uint32_t)step0;
+                        bulk_store(prices + off, buf + s * kPass, bytes);
+                        if (COUNTS) bulk_store(counts + off, buf + 2 * kPass + s * kPass, bytes);
+                        if (LOGS) bulk_store(logs + off, buf + (COUNTS ? 4 : 2) * kPass + s * kPass, bytes);
+                    }
+                }
+                bulk_commit();
+            }
+        }
+    }
+    if (lane == 0) bulk_wait_read<0>();                     // shared memory must outlive the last copies' reads
+}
+
+// ------------------------------------------------------------------------------------------
 // Nested Monte Carlo: one CTA owns one outer trajectory p and every inner path hanging off it.
 // The outer walk is trajectory_kernel's (it also leaves the exact FP32 log2-price and barrier
 // count of every point in a workspace); here the CTA reads its row of point states (400 bytes)
