@@ -321,7 +321,8 @@ def test_bullet_without_barrier_is_european(engine, orc, pkg):
 # -------------------------------------------------------------------------------- trajectories
 @pytest.mark.parametrize("n_steps,n_paths,first", [(252, 300, 0), (100, 129, 1000), (7, 33, 5), (1, 64, 0),
                                                    (33, 31, (1 << 32) - 16), (64, 1, 9), (32, 40, 0), (150, 20, 0),
-                                                   (192, 9, 7), (300, 9, 0), (600, 5, 3), (1023, 3, 1), (5000, 2, 0)])
+                                                   (192, 9, 7), (300, 9, 0), (600, 5, 3), (1023, 3, 1), (5000, 2, 0),
+                                                   (1100, 7, 2), (2048, 3, 0)])
 def test_trajectories_vs_oracle(engine, orc, pkg, n_steps, n_paths, first):
     """Path-major prices[p][i] = S(t_{i+1}) and barrier counts.  FP32 log2-space accumulation over
     n_steps steps: relative error <= ~n_steps * 2^-24 * |log2 S| ~ 1e-4 at 252 steps -> rtol 3e-4.
@@ -492,7 +493,10 @@ def test_device_info(engine):
 
 # ------------------------------------------------------------- out-of-bounds canaries (no sanitizer on this pool)
 @pytest.mark.parametrize("n_steps,n_paths", [(252, 61), (252, 24), (256, 7), (100, 33), (128, 5), (7, 5), (300, 9),
-                                             (1, 3), (37, 1), (1024, 3)])
+                                             (1, 3), (37, 1), (1024, 3),
+                                             # rows too long to stage whole: pass-by-pass staging (trajectory_long_kernel);
+                                             # an odd row count and a ragged last pass (1100 = 4 x 256 + 76)
+                                             (2048, 5), (1100, 3), (1536, 2), (4100, 1)])
 def test_trajectory_kernels_stay_inside_their_buffers(engine, pkg, n_steps, n_paths):
     """compute-sanitizer is closed on this pool, so bounds are checked with guard bands: the kernels
     (TMA slab kernel for single-pass aligned rows, general kernel otherwise, with and without
