@@ -60,6 +60,20 @@ BYTES_PER_TRAJECTORY_STEP = 4         # one float stored per path-step
 TRAJ_PATHS, TRAJ_STEPS = 1 << 20, 252
 
 
+def workload_config(n_gpus: int, scaling: str):
+    """The `config` object of BOTH arms (the reference arm times a bounded sample of this same workload and says so
+    in cpu_baseline.sample): BASELINE.json configs[1], one job of 2^30 paths (strong) or 2^30 paths per GPU (weak)."""
+    strong = scaling == "strong"
+    n_total = PATHS_PER_GPU if strong else PATHS_PER_GPU * n_gpus
+    return {"workload": "European call S0=100 K=100 r=0.05 sigma=0.2 T=1, single step, "
+                        + ("ONE job of 2^30 paths sharded over the GPUs by path index" if strong else "2^30 paths per GPU")
+                        + f" ({n_total} paths per step)",
+            "paths_per_step": n_total, "n_gpus": n_gpus, "paths_per_gpu": n_total // max(n_gpus, 1),
+            "l2": "n/a: the path reads no global memory (a path is a function of (seed, path id); 64 Ki chunk partials "
+                  "of 8 B are written per job)",
+            **CFG}
+
+
 def bs_call(S0, K, T, r, v):
     d1 = (math.log(S0 / K) + (r + 0.5 * v * v) * T) / (v * math.sqrt(T))
     d2 = d1 - v * math.sqrt(T)
@@ -262,10 +276,11 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
         "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "European call S0=100 K=100 r=0.05 sigma=0.2 T=1, single step, CPU "
-                               "simulateOptionPriceCPU (inc/tool.cuh:104-130): a bounded SAMPLE of the 2^30-path "
-                               f"workload per step ({paths} paths; the rate metric does not depend on the sample size)",
-                   "paths_per_step": paths, "full_workload_paths": PATHS_PER_GPU, **CFG},
+        "config": workload_config(args.gpus, args.scaling),
+        "reference_note": "CPU simulateOptionPriceCPU (inc/tool.cuh:104-130), unmodified, on every host core: each step "
+                          f"prices a bounded SAMPLE of the workload ({paths} paths; the rate metric does not depend on "
+                          "the sample size)",
+        "sample_paths_per_step": paths,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample,
                          "value_1core": rate1},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -434,19 +449,15 @@ def run_b200(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": warm, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
         "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"European call S0=100 K=100 r=0.05 sigma=0.2 T=1, single step, "
-                               f"{'ONE job of 2^30 paths sharded over the GPUs' if strong else '2^30 paths per GPU'} "
-                               f"({n_total} paths per step), seed {SEED}, Philox4x32-10 keyed by (seed, path id)",
-                   "paths_per_step": n_total, "paths_per_gpu": n_total // world,
+        "config": workload_config(world, args.scaling),
+        "engine": {"rng": f"seed {SEED}, Philox4x32-10 keyed by (seed, path id)",
                    "parallelism": f"path-index shards x{world}, " + (
                        "one NCCL allreduce of 1 KiB" if transport == "nccl" else
                        "one pricing launch per GPU that also folds its segments and stores them into every "
                        "rank's mailbox over NVLink (CUDA IPC), final tree on a second stream"),
                    "transport": transport,
                    "jobs_in_flight": "up to 4 (back-to-back submits" + (", consecutive jobs overlap on two pricing streams)"
-                                                                        if world > 1 else ")"),
-                   "l2": "n/a: the kernel reads no global memory (64 Ki chunk partials of 8 B written per launch)",
-                   **CFG},
+                                                                        if world > 1 else ")")},
         "gpu_launches": int(launches),
         "price": result.price, "std_error": result.std_error, "closed_form": bs_call(**CFG),
         "z_score": (result.price - bs_call(**CFG)) / result.std_error,
@@ -599,6 +610,26 @@ def other_workloads(torch, pkg, eng, hbm_gbs, peak_src):
         out[label] = {"us_per_call": 1e6 * dt0, "paths_per_s": npaths / dt0, "price": r0.price,
                       "std_error": r0.std_error, "closed_form": bs_call(**CFG),
                       "z_score": (r0.price - bs_call(**CFG)) / r0.std_error, "launches_per_call": 1}
+
+    # the optional second keying of SURVEY 8(d): path p <-> normal p & 3 of subsequence p >> 2 (four paths per Philox
+    # block).  Reported separately; the headline above is the canonical keying.
+    op = pkg.option(N_PATHS=PATHS_PER_GPU, **CFG)
+    for _ in range(3):
+        rp = eng.price_european_packed(op, PATHS_PER_GPU, SEED, pkg.CALL)
+    eng.timing_read(pkg.KERNEL_EUROPEAN_PACKED)
+    eng.timing_enable(True)
+    t0 = time.perf_counter()
+    for _ in range(10):
+        rp = eng.price_european_packed(op, PATHS_PER_GPU, SEED, pkg.CALL)
+    dtp = (time.perf_counter() - t0) / 10
+    eng.timing_enable(False)
+    pk_ms, pk_n = eng.timing_read(pkg.KERNEL_EUROPEAN_PACKED)
+    out["european_2^30_packed_keying"] = {
+        "paths_per_s": PATHS_PER_GPU / dtp, "ms_per_call": 1e3 * dtp, "kernel_ms": pk_ms / max(pk_n, 1),
+        "price": rp.price, "std_error": rp.std_error, "z_score": (rp.price - bs_call(**CFG)) / rp.std_error,
+        "bound": "XU: 3 MUFU per path -> 16/3 paths/clk/SM = 1.55e12 /s",
+        "frac": PATHS_PER_GPU / (pk_ms / max(pk_n, 1) * 1e-3) / (148 * 16 / 3 * 1.965e9),
+        "note": "synchronous public call mcb_price_european_packed (launch + sync included in paths_per_s)"}
 
     # configs[2]: 2^20 paths x 252 steps stored path-major to HBM (1.06 GB per launch > 126 MB L2)
     opt = pkg.option(N_STEPS=TRAJ_STEPS, N_PATHS=TRAJ_PATHS, B=120.0, **CFG)

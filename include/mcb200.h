@@ -107,6 +107,15 @@ int mcb_synchronize(mcb_engine *e);
 int mcb_price_european(mcb_engine *e, const mcb_option_data *opt, uint64_t n_paths, uint64_t seed,
                        int option_type, mcb_result *out);
 
+/* The same estimator under PACKED keying (no reference counterpart; SURVEY.md 8(d) lists it as the optional
+ * second keying): path p draws normal p & 3 of the stream (seed, subsequence p >> 2) -- what four successive
+ * curand_normal() calls on one state return -- so one Philox block prices four paths (about 2.5x the paths/s of the
+ * canonical keying above, which stays the default and the headline).  A different, equally valid assignment of
+ * random numbers to paths: prices agree with mcb_price_european statistically, not bit for bit.  Works on
+ * multi-device engines; results do not depend on the number of GPUs. */
+int mcb_price_european_packed(mcb_engine *e, const mcb_option_data *opt, uint64_t n_paths, uint64_t seed,
+                              int option_type, mcb_result *out);
+
 /* Bullet (barrier-count) option, N_STEPS - Tk steps, restartable from (Ik, Sk, Tk).
  * Replaces wrapper_gpu_bullet_option and wrapper_gpu_bullet_option_atomic
  * (inc/wrappers.cuh:59-93, 95-125) = simulateBulletOptionPriceMultipleBlockGPU[atomic]
@@ -246,7 +255,7 @@ uint64_t mcb_launch_count(mcb_engine *e);
  * mcb_timing_read waits for the recorded launches of `kernel`, returns their summed device
  * time and count, and forgets them. */
 enum { MCB_KERNEL_EUROPEAN = 0, MCB_KERNEL_BULLET = 1, MCB_KERNEL_TRAJECTORY = 2, MCB_KERNEL_NESTED = 3,
-       MCB_KERNEL_SWEEP = 4, MCB_KERNEL_COUNT = 5 };
+       MCB_KERNEL_SWEEP = 4, MCB_KERNEL_EUROPEAN_PACKED = 5, MCB_KERNEL_COUNT = 6 };
 int mcb_timing_enable(mcb_engine *e, int on);
 int mcb_timing_read(mcb_engine *e, int kernel, double *total_ms, uint64_t *launches);
 
@@ -273,6 +282,9 @@ int mcb_european_payoffs(mcb_engine *e, const mcb_option_data *opt, uint64_t fir
                          uint64_t seed, int option_type, float *payoffs);
 int mcb_european_chunk_partials(mcb_engine *e, const mcb_option_data *opt, uint64_t n_paths, uint64_t seed,
                                 int option_type, float *partials, uint64_t n_chunks);
+/* Per-path payoffs under packed keying (host array, n_paths floats). */
+int mcb_european_packed_payoffs(mcb_engine *e, const mcb_option_data *opt, uint64_t first_path, uint64_t n_paths,
+                                uint64_t seed, int option_type, float *payoffs);
 int mcb_bullet_payoffs(mcb_engine *e, const mcb_option_data *opt, uint64_t first_path, uint64_t n_paths,
                        uint64_t seed, int Ik, float Sk, int Tk, float *payoffs);
 /* Last segments [MCB_SEGMENTS][2] computed by a whole-job call (host array of 128 doubles). */

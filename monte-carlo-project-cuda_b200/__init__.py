@@ -37,7 +37,7 @@ HOST, DEVICE = 0, 1
 
 OK, ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_NOMEM, ERR_TIMEOUT = 0, 1, 2, 3, 4, 5
 PIPELINE_DEPTH, RESULT_RING, MAX_PEERS = 4, 8, 16
-KERNEL_EUROPEAN, KERNEL_BULLET, KERNEL_TRAJECTORY, KERNEL_NESTED, KERNEL_SWEEP = 0, 1, 2, 3, 4
+KERNEL_EUROPEAN, KERNEL_BULLET, KERNEL_TRAJECTORY, KERNEL_NESTED, KERNEL_SWEEP, KERNEL_EUROPEAN_PACKED = 0, 1, 2, 3, 4, 5
 
 
 class McbError(RuntimeError):
@@ -98,6 +98,8 @@ SIGNATURES = {
     "mcb_get_device_info": (C.c_int, [_vp, C.POINTER(DeviceInfo)]),
     "mcb_synchronize": (C.c_int, [_vp]),
     "mcb_price_european": (C.c_int, [_vp, _OP, _u64, _u64, C.c_int, _RP]),
+    "mcb_price_european_packed": (C.c_int, [_vp, _OP, _u64, _u64, C.c_int, _RP]),
+    "mcb_european_packed_payoffs": (C.c_int, [_vp, _OP, _u64, _u64, _u64, C.c_int, _vp]),
     "mcb_price_bullet": (C.c_int, [_vp, _OP, _u64, _u64, C.c_int, C.c_float, C.c_int, _RP]),
     "mcb_simulate_trajectories": (C.c_int, [_vp, _OP, _u64, _u64, _u64, _vp, _vp, C.c_int]),
     "mcb_nested_monte_carlo": (C.c_int, [_vp, _OP, _u64, _u64, _u64, _u64, C.c_int, _vp, _vp, _vp, C.c_int,
@@ -234,6 +236,18 @@ class Engine:
     def price_european(self, opt, n_paths=0, seed=1234, option_type=CALL) -> Result:
         out = Result()
         _check(self._lib.mcb_price_european(self._h, C.byref(opt), n_paths, seed, option_type, C.byref(out)))
+        return out
+
+    def price_european_packed(self, opt, n_paths=0, seed=1234, option_type=CALL) -> Result:
+        """Packed keying: path p draws normal p & 3 of subsequence p >> 2 (one Philox block per four paths)."""
+        out = Result()
+        _check(self._lib.mcb_price_european_packed(self._h, C.byref(opt), n_paths, seed, option_type, C.byref(out)))
+        return out
+
+    def european_packed_payoffs(self, opt, first_path, n_paths, seed=1234, option_type=CALL):
+        out = np.empty(n_paths, dtype=np.float32)
+        _check(self._lib.mcb_european_packed_payoffs(self._h, C.byref(opt), first_path, n_paths, seed, option_type,
+                                                     out.ctypes.data))
         return out
 
     def price_bullet(self, opt, n_paths=0, seed=1234, Ik=0, Sk=0.0, Tk=0) -> Result:

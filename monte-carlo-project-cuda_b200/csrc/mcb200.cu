@@ -1216,6 +1216,83 @@ static int threads_over_shards(mcb_engine *e, F &&body)
 }
 }  // extern "C++"
 
+// ------------------------------------------------------------------------- European, packed keying
+static int european_packed_segments_impl(mcb_engine *e, const mcb_option_data *opt, uint64_t n_paths, uint64_t seed,
+                                         int option_type, int rank, int world, double *d_segments, int write_unowned)
+{
+    DeviceGuard g(e->device);
+    cudaStream_t st = e->stream;
+    const uint64_t n_chunks = (n_paths + kEuropeanChunk - 1) / kEuropeanChunk;
+    int seg_lo, seg_hi;
+    uint64_t c_lo, c_hi;
+    segment_span(rank, world, n_chunks, &seg_lo, &seg_hi, &c_lo, &c_hi);
+    if (c_hi - c_lo > 0x7fffffffull) return fail(MCB_ERR_INVALID, "too many chunks for one launch");
+    int rc;
+    if ((rc = e->partials.reserve((size_t)(c_hi - c_lo) + 1))) return rc;
+    const EuropeanParams prm = european_params(opt, opt->K, opt->v, n_paths, seed, c_lo);
+    if (c_hi > c_lo) {
+        {
+            TimedScope timed(e, MCB_KERNEL_EUROPEAN_PACKED, st);
+            if (option_type == MCB_PUT)
+                european_packed_kernel<kPut, MCB_EUROPEAN_PATHS_PER_SLOT><<<(unsigned)(c_hi - c_lo), kSlots, 0, st>>>(
+                    prm, e->partials.ptr, nullptr, 0);
+            else
+                european_packed_kernel<kCall, MCB_EUROPEAN_PATHS_PER_SLOT><<<(unsigned)(c_hi - c_lo), kSlots, 0, st>>>(
+                    prm, e->partials.ptr, nullptr, 0);
+        }
+        e->launches++;
+        CU(cudaGetLastError());
+    }
+    return launch_segments(e, e->partials.ptr, 0, c_lo, n_chunks, seg_lo, seg_hi, 1, d_segments, st, write_unowned);
+}
+
+int mcb_price_european_packed(mcb_engine *e, const mcb_option_data *opt, uint64_t n_paths, uint64_t seed,
+                              int option_type, mcb_result *out)
+{
+    if (!out) return fail(MCB_ERR_INVALID, "out is NULL");
+    int rc = check_common(e, opt);
+    if (rc) return rc;
+    if (e->leader) return fail(MCB_ERR_INVALID, "call the multi-device engine, not one of its shards");
+    if (option_type != MCB_CALL && option_type != MCB_PUT) return fail(MCB_ERR_INVALID, "bad option_type");
+    n_paths = resolve_paths(opt, n_paths);
+    if (n_paths == 0) return fail(MCB_ERR_INVALID, "n_paths must be > 0");
+    DeviceGuard g(e->device);
+    double *dst = e->segments.ptr;
+    if ((rc = run_on_shards(e, [&](mcb_engine *s, int rank, int world) {
+             return european_packed_segments_impl(s, opt, n_paths, seed, option_type, rank, world, dst, world == 1);
+         })))
+        return rc;
+    return finish_whole_job(e, 1, n_paths, opt->r, opt->T, out);
+}
+
+int mcb_european_packed_payoffs(mcb_engine *e, const mcb_option_data *opt, uint64_t first_path, uint64_t n_paths,
+                                uint64_t seed, int option_type, float *payoffs)
+{
+    int rc = check_common(e, opt);
+    if (rc) return rc;
+    if (!payoffs) return fail(MCB_ERR_INVALID, "payoffs is NULL");
+    if (n_paths == 0) return MCB_OK;
+    DeviceGuard g(e->device);
+    const uint64_t c_lo = first_path / kEuropeanChunk;
+    const uint64_t c_hi = (first_path + n_paths + kEuropeanChunk - 1) / kEuropeanChunk;
+    if (c_hi - c_lo > 0x7fffffffull) return fail(MCB_ERR_INVALID, "too many chunks for one launch");
+    if ((rc = e->partials.reserve((size_t)(c_hi - c_lo) + 1))) return rc;
+    if ((rc = e->scratch.reserve((size_t)n_paths * sizeof(float)))) return rc;
+    float *d = reinterpret_cast<float *>(e->scratch.ptr);
+    const EuropeanParams prm = european_params(opt, opt->K, opt->v, first_path + n_paths, seed, c_lo);
+    if (option_type == MCB_PUT)
+        european_packed_kernel<kPut, MCB_EUROPEAN_PATHS_PER_SLOT><<<(unsigned)(c_hi - c_lo), kSlots, 0, e->stream>>>(
+            prm, e->partials.ptr, d, first_path);
+    else
+        european_packed_kernel<kCall, MCB_EUROPEAN_PATHS_PER_SLOT><<<(unsigned)(c_hi - c_lo), kSlots, 0, e->stream>>>(
+            prm, e->partials.ptr, d, first_path);
+    e->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(payoffs, d, (size_t)n_paths * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return MCB_OK;
+}
+
 // ---------------------------------------------------------------------------------- bullet
 static int bullet_params(const mcb_option_data *opt, uint64_t n_paths_end, uint64_t seed, int Ik, float Sk, int Tk,
                          uint64_t first_chunk, WalkParams *out)

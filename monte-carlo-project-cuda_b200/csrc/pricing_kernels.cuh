@@ -103,6 +103,79 @@ european_kernel(const __grid_constant__ EuropeanParams prm, float2 *__restrict__
 }
 
 // ------------------------------------------------------------------------------------------
+// European option under PACKED keying (SURVEY.md 8(d) "packed keying", reported separately from the canonical
+// figure): path p draws normal p & 3 of the stream (seed, subsequence p >> 2) -- the four values four successive
+// curand_normal() calls return -- so ONE Philox block prices FOUR paths: 4.25 IMAD.WIDE and 3 MUFU per path
+// instead of 16 and 4, and the bound moves from the multiplier pipe to the XU pipe (16/3 paths/clk/SM).
+// One CTA = one chunk of kSlots * PPS paths = kSlots * PPS / 4 blocks; slot t takes the chunk's blocks
+// t, t + 256, ... and accumulates each block's four paths in order, then the usual block tree.
+// ------------------------------------------------------------------------------------------
+template <int TYPE>
+__device__ __forceinline__ void packed_payoffs4(const Words4 &w, const EuropeanParams &prm, float pay[4])
+{
+    const float t0 = prm.c1 * bm_radius_unscaled(w.x), t1 = prm.c1 * bm_radius_unscaled(w.z);
+    const float v0 = bm_angle(w.y), v1 = bm_angle(w.w);
+    const float l[4] = {fmaf(t0, mufu_sin(v0), prm.c0), fmaf(t0, mufu_cos(v0), prm.c0),
+                        fmaf(t1, mufu_sin(v1), prm.c0), fmaf(t1, mufu_cos(v1), prm.c0)};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float St = mufu_ex2(l[j]);
+        pay[j] = TYPE == kPut ? fmaxf(prm.K - St, 0.0f) : fmaxf(St - prm.K, 0.0f);
+    }
+}
+
+template <int TYPE, int PPS>
+__global__ void __launch_bounds__(kSlots)
+european_packed_kernel(const __grid_constant__ EuropeanParams prm, float2 *__restrict__ partials,
+                       float *__restrict__ payoffs, uint64_t payoffs_first_path)
+{
+    static_assert(PPS % 4 == 0, "a slot takes whole Philox blocks");
+    __shared__ float scratch[2 * kWarps];
+    const uint64_t chunk = prm.first_chunk + blockIdx.x;
+    const uint64_t base = chunk * (uint64_t)(kSlots * PPS);          // first path of the chunk
+    const uint64_t sbase = base >> 2;                                 // its first subsequence (= block of four paths)
+    // a chunk's kSlots * PPS / 4 subsequences never straddle a multiple of 2^32: the high word is CTA-uniform
+    const uint32_t s_hi = (uint32_t)(sbase >> 32);
+    const uint32_t s_lo0 = (uint32_t)sbase + threadIdx.x;
+    const uint64_t left = prm.n_paths - base;                         // > 0 by construction of the grid
+
+    float sum = 0.0f, sq = 0.0f;
+    if (left >= (uint64_t)(kSlots * PPS) && payoffs == nullptr) {
+        uint64_t prod1 = (uint64_t)kPhiloxM1 * s_lo0;                 // round 0's only product, advanced by an add
+#pragma unroll 2
+        for (int i = 0; i < PPS / 4; ++i) {
+            float pay[4];
+            packed_payoffs4<TYPE>(philox_block0_from_prod(prod1, s_hi, prm.keys), prm, pay);
+            prod1 += (uint64_t)kPhiloxM1 * kSlots;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                sum = sum + pay[j];
+                sq = fmaf(pay[j], pay[j], sq);
+            }
+        }
+    } else {
+        for (int i = 0; i < PPS / 4; ++i) {
+            const uint32_t blk = (uint32_t)(i * kSlots) + threadIdx.x;     // chunk-local block
+            if ((uint64_t)blk * 4 < left) {
+                float pay[4];
+                packed_payoffs4<TYPE>(philox4x32_10(0u, 0u, s_lo0 + (uint32_t)(i * kSlots), s_hi, prm.keys), prm, pay);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint64_t local = (uint64_t)blk * 4 + (uint64_t)j;
+                    if (local < left) {
+                        sum = sum + pay[j];
+                        sq = fmaf(pay[j], pay[j], sq);
+                        if (payoffs && base + local >= payoffs_first_path) payoffs[base + local - payoffs_first_path] = pay[j];
+                    }
+                }
+            }
+        }
+    }
+    block_fold2(sum, sq, scratch);
+    if (threadIdx.x == 0) partials[blockIdx.x] = make_float2(sum, sq);
+}
+
+// ------------------------------------------------------------------------------------------
 // Batched strike/vol sweep with common random numbers (BASELINE config 5): every parameter set
 // is priced on the SAME draws, so the Philox + Box-Muller work is done once per path and only
 //   FFMA, MUFU.EX2, FADD, FMNMX, FADD, FFMA

@@ -86,6 +86,7 @@ def lib():
         L.orc_stream_normal.argtypes = [_u64, _u64, _u64]; L.orc_stream_normal.restype = C.c_double
         L.orc_stream_normals.argtypes = [_u64, _u64, _u64, _u64, _f64p]
         L.orc_european.argtypes = [P, _u64, _u64, _u64, C.c_int, _f64p, _f64p, _f32p]
+        L.orc_european_packed.argtypes = [P, _u64, _u64, _u64, C.c_int, _f64p, _f64p, _f32p]
         L.orc_bullet.argtypes = [P, _u64, _u64, _u64, C.c_int, C.c_float, C.c_int, _f64p, _f64p, _f32p]
         L.orc_trajectories.argtypes = [P, _u64, _u64, _u64, _f32p, _i32p]
         L.orc_nmc.argtypes = [P, _u64, _u64, _u64, _u64, C.c_int, _f32p, _f32p, _i32p]
@@ -184,6 +185,15 @@ def european(o, first_path, n_paths, seed=1234, option_type=CALL, want_payoffs=F
     pay = np.zeros(n_paths, dtype=np.float32) if want_payoffs else None
     lib().orc_european(C.byref(o), first_path, n_paths, seed, option_type, C.byref(s), C.byref(q),
                        _p(pay, _f32p) if want_payoffs else None)
+    return (s.value, q.value, pay) if want_payoffs else (s.value, q.value)
+
+
+def european_packed(o, first_path, n_paths, seed=1234, option_type=CALL, want_payoffs=False):
+    """Packed keying: path p draws normal p & 3 of subsequence p >> 2 (orc_european_packed)."""
+    s = C.c_double(); q = C.c_double()
+    pay = np.zeros(n_paths, dtype=np.float32) if want_payoffs else None
+    lib().orc_european_packed(C.byref(o), first_path, n_paths, seed, option_type, C.byref(s), C.byref(q),
+                              _p(pay, _f32p) if want_payoffs else None)
     return (s.value, q.value, pay) if want_payoffs else (s.value, q.value)
 
 

@@ -138,6 +138,31 @@ void orc_european(const orc_option_data *o, uint64_t first_path, uint64_t n_path
     if (sumsq) *sumsq = s2;
 }
 
+/* The same pricer under PACKED keying ("European path, packed keying"): path p draws normal
+ * p & 3 of the cuRAND stream (seed, subsequence p >> 2) -- what four successive curand_normal() calls on one
+ * state return (curand_normal.h:345-360), the reference's own way of consuming a generator
+ * (inc/trajectories.cuh:145) -- instead of normal 0 of subsequence p.  All four normals of a Philox block are
+ * used, so a path costs a quarter of a block. */
+void orc_european_packed(const orc_option_data *o, uint64_t first_path, uint64_t n_paths, uint64_t seed,
+                         int option_type, double *sum, double *sumsq, float *payoffs)
+{
+    double S0 = o->S0, K = o->K, r = o->r, sig = o->v, T = o->T;
+    double drift = (r - 0.5 * sig * sig) * T;
+    double vol = sig * sqrt(T);
+    double s = 0.0, s2 = 0.0;
+    for (uint64_t i = 0; i < n_paths; ++i) {
+        uint64_t path = first_path + i;
+        double G = orc_stream_normal(seed, path >> 2, path & 3);
+        double St = S0 * exp(drift + vol * G);
+        double p = payoff_of(St, K, option_type);
+        s += p;
+        s2 += p * p;
+        if (payoffs) payoffs[i] = (float)p;
+    }
+    if (sum) *sum = s;
+    if (sumsq) *sumsq = s2;
+}
+
 /* ------------------------------------------------------------------------------------------
  * Bullet (barrier-count) option.  Restates simulateBulletOptionPriceMultipleBlockGPU
  * (inc/trajectories.cuh:138-153) and simulateBulletOptionPriceCPU (inc/tool.cuh:155-171):

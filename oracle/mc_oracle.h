@@ -55,6 +55,8 @@ void orc_stream_normals(uint64_t seed, uint64_t subsequence, uint64_t n0, uint64
 /* ---- pricers (double maths on the float uniforms) -------------------------------- */
 void orc_european(const orc_option_data *o, uint64_t first_path, uint64_t n_paths, uint64_t seed,
                   int option_type, double *sum, double *sumsq, float *payoffs /* nullable */);
+void orc_european_packed(const orc_option_data *o, uint64_t first_path, uint64_t n_paths, uint64_t seed,
+                  int option_type, double *sum, double *sumsq, float *payoffs /* nullable */);
 void orc_bullet(const orc_option_data *o, uint64_t first_path, uint64_t n_paths, uint64_t seed,
                 int Ik, float Sk, int Tk, double *sum, double *sumsq, float *payoffs /* nullable */);
 void orc_trajectories(const orc_option_data *o, uint64_t first_path, uint64_t n_paths, uint64_t seed,

@@ -737,3 +737,60 @@ def test_two_engines_from_two_host_threads(pkg):
                 r = out[rep * 7 + i]
                 assert r.sum == want[i].sum and r.sumsq == want[i].sumsq
             assert out[rep * 7 + 6].sum == want_b.sum
+
+
+# ------------------------------------------------------------------ packed keying (optional second keying)
+@pytest.mark.parametrize("first,n", [(0, 4096), (3, 1001), (16384 - 2, 7), (5 * 16384 + 1, 40000), ((1 << 34) - 6, 13)])
+def test_packed_keying_payoffs_vs_oracle(engine, orc, pkg, first, n):
+    """Path p draws normal p & 3 of the cuRAND stream (seed, subsequence p >> 2): per-path payoffs against the
+    double-precision restatement, any first path / count (ragged blocks at both ends, a 2^32 boundary of the
+    subsequence index).  Same MUFU-based tolerance as the canonical test."""
+    for ot, oot in ((pkg.CALL, orc.CALL), (pkg.PUT, orc.PUT)):
+        got = engine.european_packed_payoffs(pkg.option(**CFG1), first, n, 1234, ot)
+        _, _, want = orc.european_packed(orc.option(**CFG1), first, n, 1234, oot, want_payoffs=True)
+        assert np.allclose(got, want, rtol=2e-5, atol=2e-4), float(np.abs(got - want).max())
+    # path 4q under packed keying == path q under canonical keying (normal 0 of subsequence q), up to one rounding
+    # of the fused multiply (the packed kernel scales the radius before the trig multiply)
+    packed = engine.european_packed_payoffs(pkg.option(**CFG1), 0, 4000, 1234, pkg.CALL)[::4]
+    canon = engine.european_payoffs(pkg.option(**CFG1), 0, 1000, 1234, pkg.CALL)
+    assert np.allclose(packed, canon, rtol=1e-5, atol=1e-4)
+
+
+def test_packed_keying_tree_and_price(engine, orc, pkg):
+    """The packed kernel's reduction: slot t of a chunk takes the chunk's Philox blocks t, t + 256, ... and adds each
+    block's four paths in order; then the same block / segment / final trees as everything else (bit-exact against
+    the oracle's trees fed with the kernel's own payoffs).  Prices: call and put within 3 SE of the closed form at
+    2^26 paths, put-call parity, agreement with the canonical keying within 4 combined SE."""
+    n = 3 * pkg.EUROPEAN_CHUNK + 1234
+    opt = pkg.option(**CFG1)
+    pay = engine.european_packed_payoffs(opt, 0, n, 1234, pkg.CALL)
+    res = engine.price_european_packed(opt, n, 1234, pkg.CALL)
+    chunk, pps = pkg.EUROPEAN_CHUNK, pkg.EUROPEAN_PATHS_PER_SLOT
+    partials = []
+    for c in range(4):
+        buf = np.zeros(chunk, dtype=np.float32)
+        cnt = min(chunk, n - c * chunk)
+        buf[:cnt] = pay[c * chunk:c * chunk + cnt]
+        # slot t, k-th accumulated path (k = 4 i + j)  <-  chunk-local path 4 (t + 256 i) + j
+        slot_major = buf.reshape(pps // 4, 256, 4).transpose(0, 2, 1).reshape(pps, 256)   # [k][t]
+        valid = (np.arange(chunk).reshape(pps // 4, 256, 4).transpose(0, 2, 1).reshape(pps, 256) < cnt)
+        s = np.zeros(256, np.float32)
+        for k in range(pps):
+            s = np.where(valid[k], (s + slot_major[k]).astype(np.float32), s)
+        # the block tree on 256 slot values = the oracle's chunk tree with one value per slot
+        ps, _ = orc.chunk_tree_f32(s, 256, 1)
+        partials.append((ps, np.float32(0.0)))
+    seg = orc.segment_tree_f64(np.array(partials, dtype=np.float32))
+    want_s, _ = orc.final_tree_f64(seg)
+    assert res.sum == want_s
+    big = 1 << 26
+    L = orc.lib()
+    call = engine.price_european_packed(opt, big, 1234, pkg.CALL)
+    put = engine.price_european_packed(opt, big, 1234, pkg.PUT)
+    exact_c = L.orc_bs_call_exact(100.0, 100.0, 1.0, 0.05, 0.2)
+    exact_p = L.orc_bs_put_exact(100.0, 100.0, 1.0, 0.05, 0.2)
+    assert abs(call.price - exact_c) < 3.0 * call.std_error and abs(put.price - exact_p) < 3.0 * put.std_error
+    assert abs((call.price - put.price) - (100.0 - 100.0 * math.exp(-0.05))) < 4.0 * (call.std_error + put.std_error)
+    canon = engine.price_european(opt, big, 1234, pkg.CALL)
+    assert abs(call.price - canon.price) < 4.0 * math.hypot(call.std_error, canon.std_error)
+    assert (call.sum, call.sumsq) == (lambda r: (r.sum, r.sumsq))(engine.price_european_packed(opt, big, 1234, pkg.CALL))

@@ -134,12 +134,14 @@ def test_multi_engine_bullet_sweep_trajectories_nested(pkg, engine, multi_engine
     n = 37 * pkg.EUROPEAN_CHUNK + 999
     ot = pkg.option(N_STEPS=252, N_PATHS=1001, B=110.0)
     nm = pkg.option(N_STEPS=12, N_PATHS=21, N_PATHS_INNER=128, B=120.0, P1=1, P2=10)
+    want_pk = engine.price_european_packed(pkg.option(), n, 1234, pkg.PUT)
     want_b = engine.price_bullet(ob, 20000, 1234)
     want_s = engine.price_sweep(pkg.option(), k, v, n, 1234, pkg.CALL)
     want_rows, want_counts = engine.simulate_trajectories(ot, 5, 1001, 1234, want_counts=True)
     want_F, want_P, want_C, want_mean = engine.nested_monte_carlo(nm, 0, 21, 1234, 1235, pkg.DISCOUNT_CORRECT)
     for multi in multi_engines:
         assert _bits(multi.price_bullet(ob, 20000, 1234)) == _bits(want_b)
+        assert _bits(multi.price_european_packed(pkg.option(), n, 1234, pkg.PUT)) == _bits(want_pk)
         got_s = multi.price_sweep(pkg.option(), k, v, n, 1234, pkg.CALL)
         assert [_bits(r) for r in got_s] == [_bits(r) for r in want_s]
         rows, counts = multi.simulate_trajectories(ot, 5, 1001, 1234, want_counts=True)
