@@ -80,3 +80,26 @@ def test_normal_moments(orc):
     assert abs((z ** 2).mean() - 1.0) < 4.0 * np.sqrt(2.0 / n)
     assert abs((z ** 3).mean()) < 4.0 * np.sqrt(15.0 / n)
     assert abs((z ** 4).mean() - 3.0) < 4.0 * np.sqrt(96.0 / n)
+
+
+def test_packed_keying_is_four_successive_curand_normals(orc, golden_philox):
+    """Packed keying: path p uses normal p & 3 of subsequence p >> 2, i.e. what four successive
+    curand_normal() calls on the state curand_init(seed, p >> 2, 0) return.  Pinned against the committed cuRAND-header
+    fixture (curand_normal sequences of several (seed, subsequence) pairs) through the oracle's packed pricer: the
+    payoff of packed path 4 s + j is the payoff of the fixture's normal j of subsequence s."""
+    o = orc.option(S0=100.0, K=100.0, r=0.05, v=0.2, T=1.0)
+    drift, vol = (0.05 - 0.5 * 0.2 * 0.2) * 1.0, 0.2
+    checked = 0
+    for v in golden_philox["curand_normals"]:
+        seed, sub = int(v["seed"]), int(v["subsequence"])
+        if sub >= 1 << 61:
+            continue
+        _, _, pay = orc.european_packed(o, 4 * sub, 4, seed, orc.CALL, want_payoffs=True)
+        want = np.maximum(100.0 * np.exp(drift + vol * np.array(v["normals"][:4])) - 100.0, 0.0)
+        np.testing.assert_allclose(pay, want, rtol=0, atol=2e-3)   # fixture normals are float32 (3e-6 apart at most)
+        checked += 1
+    assert checked >= 2
+    # packed path 4 q == canonical path q (normal 0 of subsequence q)
+    _, _, a = orc.european_packed(o, 0, 64, 1234, orc.CALL, want_payoffs=True)
+    _, _, b = orc.european(o, 0, 16, 1234, orc.CALL, want_payoffs=True)
+    assert (a[::4] == b).all()
