@@ -194,7 +194,6 @@ struct mcb_engine {
     cudaEvent_t f_done[kRing] = {};        // final pass of the job in each ring slot has finished (leader)
     cudaEvent_t t_begin = nullptr, t_end = nullptr;   // mcb_pipeline_timer_*
     HostSlot *h_ring = nullptr;            // mapped pinned: results of the last kHostRing jobs
-    uint64_t h_ring_paths[kHostRing] = {}; // n_paths of the job in each host slot (sanity)
     mcb_result *h_results = nullptr;       // pinned
     size_t h_results_cap = 0;
     double *h_segments = nullptr;          // mapped pinned, [MCB_SEGMENTS][2] of the last whole-job call
@@ -913,7 +912,6 @@ int mcb_european_submit(mcb_engine *e, const mcb_option_data *opt, uint64_t n_pa
     *ticket = epoch;
     HostSlot *hs = &e->h_ring[epoch % kHostRing];
     hs->seq = 0;                      // the job that used this slot kHostRing tickets ago expires here
-    e->h_ring_paths[epoch % kHostRing] = n_paths;
     e->ring_chunks[epoch % kHostRing] = (n_paths + kEuropeanChunk - 1) / kEuropeanChunk;
     std::atomic_thread_fence(std::memory_order_seq_cst);
     const size_t n = shard_count(e);

@@ -14,10 +14,12 @@ LIB = os.path.join(ROOT, "monte-carlo-project-cuda_b200", "libmcb200.so")
 KERNELS = {   # label -> substring of the mangled name
     "european_kernel": "european_kernelILi0ELi64ELi4E",
     "european_job_kernel": "european_job_kernelILi0ELi64E",
+    "european_packed_kernel": "european_packed_kernelILi0ELi64E",
+    "trajectory_long_kernel_prices_counts": "trajectory_long_kernelILb1ELb0ELi4E",
     "bullet_kernel": "bullet_kernelILi4E",
     "nested_kernel": "nested_kernelE",
     "sweep_kernel": "sweep_kernelILi0ELi64E",
-    "trajectory_slab_kernel_prices": "trajectory_slab_kernelILi16ELi16ELi6ELi4ELb0ELb0ELb0ELb1ELb0E",
+    "trajectory_slab_kernel_prices": "trajectory_slab_kernelILi16ELi16ELi6ELi4ELb0ELb0ELb0ELb1ELb1E",
     "trajectory_slab_kernel_prices_counts_fast": "trajectory_slab_kernelILi16ELi16ELi4ELi4ELb1ELb0ELb0ELb1ELb1E",
     "segments_job_kernel": "segments_job_kernelE",
     "combine_job_kernel": "combine_job_kernelE",
