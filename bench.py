@@ -427,6 +427,7 @@ def run_b200(args):
     barrier()
     e2e_value = e2e_s = None
     e2e_res = None
+    multi_sweep = None
     if rank == 0:
         e2e_eng = eng if world == 1 else pkg.Engine(list(range(world)))
         for _ in range(3):
@@ -436,6 +437,21 @@ def run_b200(args):
             e2e_res = e2e_eng.price_european(opt, n_total, SEED, pkg.CALL)
         e2e_s = time.perf_counter() - t0
         e2e_value = n_total * args.steps / e2e_s
+        if world > 1 and not args.headline_only:
+            # BASELINE configs[4] through the SAME single-process engine (synchronous C-ABI call, host arrays in, host
+            # results out; the segments of the other shards cross NVLink as peer stores from segment_sets_kernel)
+            import numpy as np
+            K, V = np.meshgrid(np.linspace(60, 140, 32, dtype=np.float32), np.linspace(0.05, 0.8, 32, dtype=np.float32),
+                               indexing="ij")
+            k, v = K.ravel().copy(), V.ravel().copy()
+            e2e_eng.price_sweep(opt, k, v, 1 << 26, SEED, pkg.CALL)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                sw = e2e_eng.price_sweep(opt, k, v, 1 << 26, SEED, pkg.CALL)
+            dt = (time.perf_counter() - t0) / 3
+            multi_sweep = {"ms": 1e3 * dt, "path_params_per_s": 1024 * (1 << 26) / dt,
+                           "price_hex": hexbits(sw[16 * 32 + 6].price),
+                           "api": f"mcb_price_sweep on mcb_engine_create_multi({world} GPUs), rank 0, synchronous"}
         if world > 1:
             e2e_eng.close()
     if world > 1:
@@ -524,6 +540,8 @@ def run_b200(args):
         barrier()
         t_sweep = max_over_ranks(float(s0.elapsed_time(s1))) * 1e-3 / reps
         res = pricer._fetch(1024)
+        if multi_sweep:
+            line["other_workloads"]["sweep_1024x2^26_one_engine_e2e"] = multi_sweep
         line["other_workloads"]["sweep_1024x2^26_sharded"] = {
             "path_params_per_s": 1024 * (1 << 26) / t_sweep, "ms": 1e3 * t_sweep, "scaling": "strong",
             "collective": "one NCCL all-reduce of 1024 x 64 x 2 doubles (1 MiB)",
