@@ -1175,16 +1175,36 @@ template <typename F>
 static int run_on_shards(mcb_engine *e, F &&enqueue)
 {
     const size_t n = shard_count(e);
-    int rc;
-    for (size_t i = 0; i < n; ++i) {
-        mcb_engine *s = shard_at(e, i);
+    // every shard's launcher thread enqueues its own device (parameter staging + launches + its event) while this
+    // thread does the leader's; then the leader's stream waits for the shards' events
+    auto one = [&](mcb_engine *s, size_t i) -> int {
         DeviceGuard g(s->device);
-        if ((rc = enqueue(s, (int)i, (int)n))) return rc;
-        if (i) {
-            CU(cudaEventRecord(s->p_done[0], s->stream));
-            CU(cudaStreamWaitEvent(e->stream, s->p_done[0], 0));
+        int rc = enqueue(s, (int)i, (int)n);
+        if (rc == MCB_OK && i) {
+            cudaError_t err = cudaEventRecord(s->p_done[0], s->stream);
+            if (err != cudaSuccess) rc = fail(MCB_ERR_CUDA, "cudaEventRecord failed: %s", cudaGetErrorString(err));
         }
+        return rc;
+    };
+    for (size_t i = 1; i < n; ++i) {
+        mcb_engine *s = shard_at(e, i);
+        if (!s->worker) continue;
+        s->worker->post([&one, s, i]() {
+            const int r = one(s, i);
+            if (r != MCB_OK) s->worker->message = g_error;
+            return r;
+        });
     }
+    int rc = one(e, 0);
+    for (size_t i = 1; i < n; ++i) {
+        mcb_engine *s = shard_at(e, i);
+        const int r = s->worker ? s->worker->wait() : one(s, i);
+        if (r != MCB_OK && rc == MCB_OK)
+            rc = s->worker ? fail(r, "shard %zu (device %d): %s", i, s->device, s->worker->message.c_str()) : r;
+    }
+    if (rc) return rc;
+    DeviceGuard g(e->device);
+    for (size_t i = 1; i < n; ++i) CU(cudaStreamWaitEvent(e->stream, shard_at(e, i)->p_done[0], 0));
     return MCB_OK;
 }
 }  // extern "C++"
