@@ -19,6 +19,47 @@ import ctypes as C
 from . import (CALL, SEGMENTS, Engine, McbError, Result, path_span)  # noqa: F401  (re-exported helpers)
 
 
+def connect_peer_mailboxes(engine, dist, group, rank: int, world: int, strict: bool = False) -> bool:
+    """CUDA-IPC mailbox exchange of a process group; EVERY rank ends up in the same mode.
+
+    Each rank exports its mailbox and reports its job epoch; handles and epochs are all-gathered; every rank
+    connects with the MAXIMUM epoch (a fresh or lagging engine can then neither satisfy nor block a wait of the
+    group's jobs); the outcomes are all-gathered again (that is also the barrier between mapping and the first peer
+    store).  If ANY rank failed anywhere, every rank goes back to a group of one (its engine keeps pricing on its
+    own) and the function returns False -- the caller then uses the all-reduce route -- or raises when ``strict``.
+    Pure host logic over ``dist`` and the engine's four peer_* methods (tests/test_dist_gloo.py drives it on CPU
+    with stand-in engines)."""
+    mine = {"handle": None, "epoch": engine.peer_epoch(), "error": None}
+    try:
+        if world > 16:
+            raise McbError(1, "the peer transport supports at most 16 ranks")
+        mine["handle"] = engine.peer_mailbox_create()
+    except McbError as exc:
+        mine["error"] = str(exc)
+    everyone = [None] * world
+    dist.all_gather_object(everyone, mine, group=group)
+    ok = all(x["error"] is None for x in everyone)
+    base = max(x["epoch"] for x in everyone)
+    err = None
+    if ok:
+        try:
+            engine.peer_mailbox_connect(rank, world, [x["handle"] for x in everyone], base)
+        except McbError as exc:
+            err = str(exc)
+    results = [None] * world
+    dist.all_gather_object(results, err, group=group)   # also the barrier after connect
+    ok = ok and all(x is None for x in results)
+    if not ok:
+        # back to a group of one, so that engine.price_european keeps working on this rank (a group of one maps
+        # nothing: its handle slot is never opened, so a rank whose export failed can pass a blank one)
+        engine.peer_mailbox_connect(0, 1, [mine["handle"] or bytes(64)], engine.peer_epoch())
+        if strict:
+            raise McbError(2, "peer transport unavailable: " + "; ".join(
+                str(x) for x in ([y["error"] for y in everyone] + results) if x))
+    dist.barrier(group=group)
+    return ok
+
+
 class ShardedPricer:
     """European / bullet / sweep pricing over the ranks of a ``torch.distributed`` group.
 
@@ -66,36 +107,7 @@ class ShardedPricer:
             self.transport = "peer" if self._connect_peers(strict=transport == "peer") else "nccl"
 
     def _connect_peers(self, strict: bool) -> bool:
-        """CUDA-IPC mailbox exchange; every rank ends up in the same mode."""
-        dist, eng = self.dist, self.engine
-        mine = {"handle": None, "epoch": eng.peer_epoch(), "error": None}
-        try:
-            if self.world > 16:
-                raise McbError(1, "the peer transport supports at most 16 ranks")
-            mine["handle"] = eng.peer_mailbox_create()
-        except McbError as exc:
-            mine["error"] = str(exc)
-        everyone = [None] * self.world
-        dist.all_gather_object(everyone, mine, group=self.group)
-        ok = all(x["error"] is None for x in everyone)
-        base = max(x["epoch"] for x in everyone)
-        err = None
-        if ok:
-            try:
-                eng.peer_mailbox_connect(self.rank, self.world, [x["handle"] for x in everyone], base)
-            except McbError as exc:
-                err = str(exc)
-        results = [None] * self.world
-        dist.all_gather_object(results, err, group=self.group)   # also the barrier after connect
-        ok = ok and all(x is None for x in results)
-        if not ok:
-            # back to a group of one, so that engine.price_european keeps working on this rank
-            eng.peer_mailbox_connect(0, 1, [eng.peer_mailbox_create()], eng.peer_epoch())
-            if strict:
-                raise McbError(2, "peer transport unavailable: " + "; ".join(
-                    str(x) for x in ([y["error"] for y in everyone] + results) if x))
-        dist.barrier(group=self.group)
-        return ok
+        return connect_peer_mailboxes(self.engine, self.dist, self.group, self.rank, self.world, strict)
 
     def _reserve(self, n_sets: int):
         t = self.torch

@@ -102,3 +102,68 @@ def test_trajectory_slabs_concatenate_to_the_single_rank_result(tmp_path, world,
     prices, counts = orc.trajectories(orc.option(N_STEPS=16, N_PATHS=n_paths, B=120.0), 0, n_paths, 1234)
     assert (np.load(tmp_path / "prices.npy").view(np.uint32) == prices.view(np.uint32)).all()
     assert (np.load(tmp_path / "counts.npy") == counts).all()
+
+
+class _StandInEngine:
+    """The four peer_* methods of Engine without a GPU: records what the host logic asks of it."""
+
+    def __init__(self, pkg, rank, epoch, fail_create=False, fail_connect=False):
+        self.pkg, self.rank, self.epoch = pkg, rank, epoch
+        self.fail_create, self.fail_connect = fail_create, fail_connect
+        self.calls = []
+
+    def peer_epoch(self):
+        return self.epoch
+
+    def peer_mailbox_create(self):
+        if self.fail_create:
+            raise self.pkg.McbError(2, "cudaIpcGetMemHandle failed (stand-in)")
+        return bytes([self.rank]) * 64
+
+    def peer_mailbox_connect(self, rank, world, handles, base_epoch):
+        if self.fail_connect and world > 1:
+            raise self.pkg.McbError(2, "cudaIpcOpenMemHandle failed (stand-in)")
+        self.calls.append((rank, world, [h[0] for h in handles], base_epoch))
+        self.epoch = max(self.epoch, base_epoch)
+
+
+def _connect_worker(rank, world, port, scenario, out_dir):
+    sys.path.insert(0, ROOT)
+    import importlib
+    import json
+    import __graft_entry__ as entry
+    pkg = entry.load_package()
+    sharded = importlib.import_module(entry.PKG_NAME + ".sharded")
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        eng = _StandInEngine(pkg, rank, epoch=10 * (rank + 1),
+                             fail_create=(scenario == "create" and rank == 1),
+                             fail_connect=(scenario == "connect" and rank == 0))
+        ok = sharded.connect_peer_mailboxes(eng, dist, None, rank, world, strict=False)
+        with open(os.path.join(out_dir, f"c{rank}.json"), "w") as f:
+            json.dump({"ok": ok, "calls": eng.calls, "epoch": eng.epoch}, f)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("scenario", ["fine", "create", "connect"])
+def test_peer_transport_agreement_over_gloo(tmp_path, scenario, pkg):
+    """The host side of the CUDA-IPC job pipeline (sharded.connect_peer_mailboxes) with world 3 over gloo and
+    stand-in engines: all ranks connect with every handle in rank order and the MAXIMUM epoch; if any rank fails to
+    export or to map a mailbox, EVERY rank falls back to a group of one (so no rank ever waits for a peer that is
+    not in its group) and reports False."""
+    import json
+    world = 3
+    port = 33500 + (os.getpid() % 2000) + {"fine": 0, "create": 1, "connect": 2}[scenario]
+    mp.spawn(_connect_worker, args=(world, port, scenario, str(tmp_path)), nprocs=world, join=True)
+    got = [json.load(open(tmp_path / f"c{r}.json")) for r in range(world)]
+    if scenario == "fine":
+        for r, g in enumerate(got):
+            assert g["ok"] is True and g["calls"] == [[r, world, [0, 1, 2], 30]] and g["epoch"] == 30
+    else:
+        for r, g in enumerate(got):
+            assert g["ok"] is False
+            assert g["calls"][-1][:2] == [0, 1]          # back to a group of one, on every rank
+            assert all(c[1] == 1 for c in g["calls"]) or scenario == "connect"
