@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Small fixed workloads for ncu captures (run plain first, then the same command under ncu).
 
-    python tools/profile_target.py european|trajectory|bullet|nested|sweep [reps]
+    python tools/profile_target.py european|packed|trajectory|trajectory_long|bullet|nested|sweep [reps]
 """
 import os
 import sys
@@ -27,6 +27,16 @@ for _ in range(reps):
         eng._lib.mcb_simulate_trajectories(eng._h, pkg.option(N_STEPS=steps, N_PATHS=n, B=120.0, **CFG), 0, n, 1234,
                                            buf.data_ptr(), None, pkg.DEVICE)
         print(float(buf[-1]))
+    elif what == "packed":
+        print(eng.price_european_packed(pkg.option(**CFG), 1 << 30, 1234, pkg.CALL))
+    elif what == "trajectory_long":
+        import torch
+        n, steps = 1 << 18, 2048
+        buf = torch.empty(n * steps, dtype=torch.float32, device="cuda:0")
+        cnt = torch.empty(n * steps, dtype=torch.int32, device="cuda:0")
+        eng._lib.mcb_simulate_trajectories(eng._h, pkg.option(N_STEPS=steps, N_PATHS=n, B=120.0, **CFG), 0, n, 1234,
+                                           buf.data_ptr(), cnt.data_ptr(), pkg.DEVICE)
+        print(float(buf[-1]), int(cnt[-1]))
     elif what == "bullet":
         print(eng.price_bullet(pkg.option(N_STEPS=100, N_PATHS=1 << 22, B=120.0, **CFG), 1 << 22, 1234))
     elif what == "nested":
