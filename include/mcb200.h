@@ -204,6 +204,8 @@ int mcb_nested_async(mcb_engine *e, const mcb_option_data *opt, uint64_t first_o
                      float *d_prices, int *d_counts, void *stream);
 
 /* ---- the European job pipeline: ONE launch per price, results through mapped host memory --------
+ * (a shard of 2^26 paths or more prices with the plain kernel plus one small segment launch: the ticket that
+ * makes the single launch possible costs more than a launch there)
  * mcb_price_european is submit + collect.  A job is priced by the engine's group of shards:
  *   - a plain engine: one shard.  The pricing kernel's last CTA folds the segments, runs the final
  *     tree and writes the mcb_result into pinned host memory: one launch, no copy, no stream sync
@@ -226,7 +228,7 @@ int mcb_european_submit(mcb_engine *e, const mcb_option_data *opt, uint64_t n_pa
                         int option_type, uint64_t *ticket);
 int mcb_european_collect(mcb_engine *e, uint64_t ticket, mcb_result *out);
 /* Device time of a batch of pipelined jobs: start drains every stream and records an event,
- * stop records one behind everything submitted since (all shards, both streams), waits for it and
+ * stop records one behind everything submitted since (all shards, all of their streams), waits for it and
  * returns the elapsed milliseconds (CUDA events on the launching streams). */
 int mcb_pipeline_timer_start(mcb_engine *e);
 int mcb_pipeline_timer_stop(mcb_engine *e, double *elapsed_ms);
