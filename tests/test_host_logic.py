@@ -144,3 +144,24 @@ def test_product_never_imports_oracle():
         for f in files:
             text = open(os.path.join(dirpath, f)).read()
             assert not any("#include" in ln and "oracle" in ln for ln in text.splitlines()), f
+
+
+def test_python_constants_match_the_header(pkg):
+    """The binding's constants are the header's macros / enumerators (geometry of the reduction, pipeline depths,
+    status codes, kernel ids): a drift here would silently mis-size buffers or mis-read statuses."""
+    text = open(os.path.join(ROOT, "include", "mcb200.h")).read()
+    macro = lambda name: int(re.search(r"#define\s+%s\s+(\d+)" % name, text).group(1))
+    assert macro("MCB_SLOTS") == pkg.SLOTS and macro("MCB_SEGMENTS") == pkg.SEGMENTS
+    assert macro("MCB_EUROPEAN_PATHS_PER_SLOT") == pkg.EUROPEAN_PATHS_PER_SLOT
+    assert macro("MCB_BULLET_PATHS_PER_SLOT") == pkg.BULLET_PATHS_PER_SLOT
+    assert macro("MCB_PIPELINE_DEPTH") == pkg.PIPELINE_DEPTH and macro("MCB_RESULT_RING") == pkg.RESULT_RING
+    assert macro("MCB_MAX_PEERS") == pkg.MAX_PEERS and macro("MCB_IPC_HANDLE_BYTES") == 64
+    enum = lambda name: int(re.search(r"\b%s\s*=\s*(\d+)" % name, text).group(1))
+    for name, value in (("MCB_OK", pkg.OK), ("MCB_ERR_INVALID", pkg.ERR_INVALID), ("MCB_ERR_CUDA", pkg.ERR_CUDA),
+                        ("MCB_ERR_NO_DEVICE", pkg.ERR_NO_DEVICE), ("MCB_ERR_NOMEM", pkg.ERR_NOMEM),
+                        ("MCB_ERR_TIMEOUT", pkg.ERR_TIMEOUT), ("MCB_KERNEL_EUROPEAN", pkg.KERNEL_EUROPEAN),
+                        ("MCB_KERNEL_SWEEP", pkg.KERNEL_SWEEP), ("MCB_KERNEL_EUROPEAN_PACKED", pkg.KERNEL_EUROPEAN_PACKED),
+                        ("MCB_CALL", pkg.CALL), ("MCB_PUT", pkg.PUT), ("MCB_HOST", pkg.HOST), ("MCB_DEVICE", pkg.DEVICE)):
+        assert enum(name) == value, name
+    assert pkg.Result.__dict__ is not None and __import__("ctypes").sizeof(pkg.Result) == 40
+    assert __import__("ctypes").sizeof(pkg.OptionData) == 48
