@@ -1,7 +1,8 @@
 """Stress of the job pipeline over CUDA-IPC mailboxes (run under torchrun, one process per GPU):
 thousands of small and mid-size jobs submitted back to back (ring wrap-arounds, acks, both pricing streams, empty
 shards), every result compared bit for bit with a single-GPU engine of the same process.
-    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/stress_pipeline.py [jobs]"""
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/stress_pipeline.py [jobs]
+Run with plain `python` it stresses ONE engine handle over every GPU of the process instead (launcher threads, events)."""
 import os
 import sys
 
@@ -14,15 +15,21 @@ import torch.distributed as dist
 
 import __graft_entry__ as entry
 
-rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
-torch.cuda.set_device(local)
-dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 pkg = entry.load_package()
-sharded = importlib.import_module(entry.PKG_NAME + ".sharded")
 jobs = int(sys.argv[1]) if len(sys.argv) > 1 else 4000
-eng = pkg.Engine(local)
-solo = pkg.Engine(local)
-pricer = sharded.ShardedPricer(eng, transport="peer")
+INPROC = "RANK" not in os.environ                  # plain `python`: ONE engine over every GPU of the process
+if INPROC:
+    rank, world, local = 0, torch.cuda.device_count(), 0
+    eng = pkg.Engine(list(range(world)))
+    solo = pkg.Engine(0)
+else:
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    sharded = importlib.import_module(entry.PKG_NAME + ".sharded")
+    eng = pkg.Engine(local)
+    solo = pkg.Engine(local)
+    pricer = sharded.ShardedPricer(eng, transport="peer")
 sizes = [1, 100_000, 16384 * 63 + 5, 16384 * 200 + 999, 1 << 22, 16384 * 4100 + 3]
 bad = 0
 pending = []
@@ -41,10 +48,13 @@ for t, n0, k0, s0, ty0 in pending:
     want = solo.price_european(pkg.option(K=k0), n0, s0, ty0)
     bad += (got.sum, got.sumsq, got.price) != (want.sum, want.sumsq, want.price)
 flag = torch.tensor([bad, eng.peer_timeouts()], dtype=torch.int64, device="cuda")
-dist.all_reduce(flag)
+if not INPROC:
+    dist.all_reduce(flag)
 if rank == 0:
-    print(f"stress: {jobs} jobs on {world} ranks, mismatches {int(flag[0])}, timeouts {int(flag[1])}")
+    shape = "one engine over %d GPUs" % world if INPROC else "%d ranks" % world
+    print(f"stress: {jobs} jobs on {shape}, mismatches {int(flag[0])}, timeouts {int(flag[1])}")
 eng.close()
 solo.close()
-dist.destroy_process_group()
+if not INPROC:
+    dist.destroy_process_group()
 sys.exit(1 if int(flag[0]) or int(flag[1]) else 0)
