@@ -190,6 +190,7 @@ struct mcb_engine {
     mcb_engine *leader = nullptr;          // sub-engine of a multi-device engine: its leader
     unsigned long long job_epoch = 0;      // jobs submitted so far (leader / single engine)
     unsigned long long timeout_ns = 10ull * 1000000000ull;   // bound of every device-side wait
+    bool small_jobs = true;                // jobs of <= 64 chunks take the cluster kernel (MCB_SMALL_JOBS=0: tools only)
     cudaEvent_t p_done[kRing] = {};        // pricing launch of the job in each ring slot has finished (this shard)
     cudaEvent_t f_done[kRing] = {};        // final pass of the job in each ring slot has finished (leader)
     cudaEvent_t t_begin = nullptr, t_end = nullptr;   // mcb_pipeline_timer_*
@@ -558,6 +559,7 @@ static int engine_create_one(int device, mcb_engine **out)
     }
     memset(e->h_segments, 0, sizeof(double) * (2 * MCB_SEGMENTS + 8));
     memset(e->h_ring, 0, sizeof(HostSlot) * kHostRing);
+    e->small_jobs = env_int("MCB_SMALL_JOBS", 1) != 0;
     e->peers.box[0] = e->mailbox;
     if (e->segments.reserve(2 * MCB_SEGMENTS + 8) || reserve_results(e, 1)) {
         mcb_engine_destroy(e);
@@ -727,7 +729,7 @@ int mcb_synchronize(mcb_engine *e)
 // --------------------------------------------------------------- peer-memory exchange (NVLink)
 static_assert(MCB_MAX_PEERS == kMaxPeers && MCB_IPC_HANDLE_BYTES == sizeof(cudaIpcMemHandle_t), "peer ABI");
 static_assert(MCB_PIPELINE_DEPTH == kRing && MCB_RESULT_RING == kHostRing, "pipeline ABI");
-static_assert(sizeof(HostSlot) == 64, "one result slot per 64-byte line");
+static_assert(sizeof(HostSlot) == 128, "one result slot per 128-byte line");
 
 int mcb_peer_mailbox_create(mcb_engine *e, void *handle_out)
 {
@@ -818,6 +820,27 @@ int mcb_peer_timeouts(mcb_engine *e, uint64_t *count)
 // ---------------------------------------------------------------- the European job pipeline
 namespace {
 
+// Host side of HostSlot's flag-in-data format (pricing_kernels.cuh): a result is complete once all ten words carry
+// the ticket's tag; a slot is expired by giving every word a tag that cannot match.
+bool host_slot_read(const volatile HostSlot *hs, unsigned long long ticket, ResultDev *out)
+{
+    const unsigned long long tag = ticket & 0xffffffffull;
+    unsigned long long f[5];
+    for (int k = 0; k < 5; ++k) {
+        const unsigned long long lo = hs->w[2 * k], hi = hs->w[2 * k + 1];   // aligned 8-byte loads: never torn
+        if ((lo >> 32) != tag || (hi >> 32) != tag) return false;
+        f[k] = (lo & 0xffffffffull) | (hi << 32);
+    }
+    memcpy(out, f, sizeof(f));
+    return true;
+}
+
+void host_slot_expire(HostSlot *hs, unsigned long long epoch)
+{
+    const unsigned long long never = (~epoch & 0xffffffffull) << 32;
+    for (int k = 0; k < 10; ++k) *(volatile unsigned long long *)&hs->w[k] = never;
+}
+
 // One shard's launch of job `epoch`: european_job_kernel over the chunks it owns (or the publish-only
 // kernel when it owns none), on the shard's main stream.
 int submit_shard(mcb_engine *s, mcb_engine *L, const mcb_option_data *opt, uint64_t n_paths, uint64_t seed,
@@ -874,6 +897,15 @@ int submit_shard(mcb_engine *s, mcb_engine *L, const mcb_option_data *opt, uint6
                                                                st)))
             return rc;
         segments_job_kernel<<<(unsigned)(seg_hi - seg_lo), kSlots, 0, st>>>(args, partials.ptr, c_lo);
+    } else if (c_hi > c_lo && n_chunks <= kSmallJobChunks && s->small_jobs) {
+        // small job: a cluster of eight CTAs per chunk (latency, see european_small_job_kernel)
+        const EuropeanParams prm = european_params(opt, opt->K, opt->v, n_paths, seed, c_lo);
+        TimedScope timed(s, MCB_KERNEL_EUROPEAN, st);
+        const unsigned grid = (unsigned)(c_hi - c_lo) * kSmallCluster;
+        if (option_type == MCB_PUT)
+            european_small_job_kernel<kPut, MCB_EUROPEAN_PATHS_PER_SLOT><<<grid, kSlots, 0, st>>>(prm, args, partials.ptr);
+        else
+            european_small_job_kernel<kCall, MCB_EUROPEAN_PATHS_PER_SLOT><<<grid, kSlots, 0, st>>>(prm, args, partials.ptr);
     } else if (c_hi > c_lo) {
         const EuropeanParams prm = european_params(opt, opt->K, opt->v, n_paths, seed, c_lo);
         TimedScope timed(s, MCB_KERNEL_EUROPEAN, st);
@@ -911,7 +943,7 @@ int mcb_european_submit(mcb_engine *e, const mcb_option_data *opt, uint64_t n_pa
     const unsigned long long epoch = ++e->job_epoch;
     *ticket = epoch;
     HostSlot *hs = &e->h_ring[epoch % kHostRing];
-    hs->seq = 0;                      // the job that used this slot kHostRing tickets ago expires here
+    host_slot_expire(hs, epoch);      // the job that used this slot kHostRing tickets ago expires here
     e->ring_chunks[epoch % kHostRing] = (n_paths + kEuropeanChunk - 1) / kEuropeanChunk;
     std::atomic_thread_fence(std::memory_order_seq_cst);
     const size_t n = shard_count(e);
@@ -960,7 +992,8 @@ int mcb_european_collect(mcb_engine *e, uint64_t ticket, mcb_result *out)
     // (no cudaStreamSynchronize round trip); every so often make sure the streams are still healthy.
     const auto t0 = std::chrono::steady_clock::now();
     unsigned long long spins = 0;
-    while (hs->seq != ticket) {
+    ResultDev got;
+    while (!host_slot_read(hs, ticket, &got)) {
         if ((++spins & 0x3fff) == 0) {
             DeviceGuard g(e->device);
             cudaError_t qa = cudaStreamQuery(e->stream), qb = cudaStreamQuery(e->f_stream);
@@ -976,9 +1009,9 @@ int mcb_european_collect(mcb_engine *e, uint64_t ticket, mcb_result *out)
                     idle = cudaStreamQuery(shard_at(e, i)->stream) == cudaSuccess &&
                            cudaStreamQuery(shard_at(e, i)->stream2) == cudaSuccess;
                 }
-                if (idle && hs->seq != ticket) {
+                if (idle && !host_slot_read(hs, ticket, &got)) {
                     std::atomic_thread_fence(std::memory_order_seq_cst);
-                    if (hs->seq != ticket)
+                    if (!host_slot_read(hs, ticket, &got))
                         return fail(MCB_ERR_CUDA, "the streams are idle but ticket %llu never completed",
                                     (unsigned long long)ticket);
                 }
@@ -990,8 +1023,7 @@ int mcb_european_collect(mcb_engine *e, uint64_t ticket, mcb_result *out)
         __builtin_ia32_pause();
 #endif
     }
-    std::atomic_thread_fence(std::memory_order_acquire);
-    memcpy(out, const_cast<const ResultDev *>(&hs->result), sizeof(mcb_result));
+    memcpy(out, &got, sizeof(mcb_result));
     e->last_job_epoch = ticket;
     e->last_job_chunks = e->ring_chunks[ticket % kHostRing];
     if (out->n_paths == 0 || out->price != out->price)

@@ -598,6 +598,9 @@ segment_sets_kernel(const float2 *__restrict__ partials, uint64_t partials_strid
 // lets a shard run kRing - 1 jobs ahead of the slowest consumer.
 // The cold tail lives in a __noinline__ function so that the hot loop keeps its 8 CTAs per SM.
 // ------------------------------------------------------------------------------------------
+#ifndef MCB_TRACE                 // tools/job_latency_probe.cu defines it to stamp clock64() along the one-CTA job
+#define MCB_TRACE(i)
+#endif
 constexpr int kMaxPeers = 16;  // MCB_MAX_PEERS
 constexpr int kRing = 4;       // MCB_PIPELINE_DEPTH: mailbox slots = jobs in flight per engine
 
@@ -611,11 +614,29 @@ struct PeerTable {
     PeerMailbox *box[kMaxPeers];                       // box[r] = shard r's mailbox as mapped here
 };
 
-struct HostSlot {              // mapped pinned host memory, one per job in flight (64 bytes)
-    ResultDev result;
-    unsigned long long seq;    // == epoch once `result` is complete (written last, after a system fence)
-    unsigned long long pad[2];
+// Result slot in mapped pinned host memory, one per job in flight.  The five 8-byte fields of ResultDev travel as ten
+// words of (data half | job tag << 32): every 8-byte store is a complete message, so the kernel needs NO system fence
+// between "data" and "flag" (fence.sys costs 1.4 us here, tools/launch_floor.cu) and the host accepts the result once
+// all ten words carry the job's tag -- the flag-in-data scheme of the low-latency protocols of collective libraries.
+struct HostSlot {
+    unsigned long long w[10];  // w[2k] = low half of field k, w[2k + 1] = high half, tag = low 32 bits of the epoch
+    unsigned long long pad[6];
 };
+
+__device__ __forceinline__ void host_publish(HostSlot *h, const ResultDev &r, unsigned long long epoch)
+{
+    const unsigned long long tag = (epoch & 0xffffffffull) << 32;
+    const unsigned long long f[5] = {(unsigned long long)__double_as_longlong(r.price),
+                                     (unsigned long long)__double_as_longlong(r.std_error),
+                                     (unsigned long long)__double_as_longlong(r.sum),
+                                     (unsigned long long)__double_as_longlong(r.sumsq), (unsigned long long)r.n_paths};
+    volatile unsigned long long *w = h->w;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        w[2 * k] = tag | (f[k] & 0xffffffffull);
+        w[2 * k + 1] = tag | (f[k] >> 32);
+    }
+}
 
 struct JobArgs {
     uint64_t n_chunks;              // chunks of the WHOLE job (segment boundaries are global)
@@ -665,16 +686,14 @@ __device__ __forceinline__ bool segment_is_empty(uint64_t n_chunks, int seg)
     return (n_chunks * (uint64_t)seg) / kSegments == (n_chunks * (uint64_t)(seg + 1)) / kSegments;
 }
 
-__device__ __forceinline__ void final_tree_warp(const volatile double *seg, int lane, uint64_t n_chunks, uint64_t n_paths,
-                                                double discount, bool ok, unsigned long long epoch, ResultDev *d_out,
-                                                HostSlot *h_out)
+// (s, q) = this lane's first-level pair sums (segments lane and lane + 32)
+__device__ __forceinline__ void final_tree_finish(double s, double q, int lane, uint64_t n_paths, double discount, bool ok,
+                                                  unsigned long long epoch, ResultDev *d_out, HostSlot *h_out)
 {
-    const bool lo_live = !segment_is_empty(n_chunks, lane), hi_live = !segment_is_empty(n_chunks, lane + 32);
-    double s = (lo_live ? seg[2 * lane] : 0.0) + (hi_live ? seg[2 * (lane + 32)] : 0.0);
-    double q = (lo_live ? seg[2 * lane + 1] : 0.0) + (hi_live ? seg[2 * (lane + 32) + 1] : 0.0);
     s = warp_fold(s);
     q = warp_fold(q);
     if (lane == 0) {
+        MCB_TRACE(5)
         const double n = (double)n_paths;
         const double mean = s / n;
         double var = q / n - mean * mean;
@@ -687,18 +706,23 @@ __device__ __forceinline__ void final_tree_warp(const volatile double *seg, int 
         r.sum = ok ? s : nan;
         r.sumsq = ok ? q : nan;
         r.n_paths = ok ? n_paths : 0;
+        MCB_TRACE(6)
         if (d_out) *d_out = r;
         if (h_out) {
-            volatile double *hd = reinterpret_cast<volatile double *>(&h_out->result);
-            hd[0] = r.price;
-            hd[1] = r.std_error;
-            hd[2] = r.sum;
-            hd[3] = r.sumsq;
-            *reinterpret_cast<volatile unsigned long long *>(&h_out->result.n_paths) = r.n_paths;
-            __threadfence_system();
-            *reinterpret_cast<volatile unsigned long long *>(&h_out->seq) = epoch;
+            host_publish(h_out, r, epoch);
+            MCB_TRACE(7)
         }
     }
+}
+
+__device__ __forceinline__ void final_tree_warp(const volatile double *seg, int lane, uint64_t n_chunks, uint64_t n_paths,
+                                                double discount, bool ok, unsigned long long epoch, ResultDev *d_out,
+                                                HostSlot *h_out)
+{
+    const bool lo_live = !segment_is_empty(n_chunks, lane), hi_live = !segment_is_empty(n_chunks, lane + 32);
+    const double s = (lo_live ? seg[2 * lane] : 0.0) + (hi_live ? seg[2 * (lane + 32)] : 0.0);
+    const double q = (lo_live ? seg[2 * lane + 1] : 0.0) + (hi_live ? seg[2 * (lane + 32) + 1] : 0.0);
+    final_tree_finish(s, q, lane, n_paths, discount, ok, epoch, d_out, h_out);
 }
 
 // Store segment `seg` = (a, b) of this shard into every consumer's mailbox slot, and -- in the CTA that
@@ -724,9 +748,10 @@ __device__ __forceinline__ void job_publish_segment(const JobArgs &args, int seg
         flag[1] = atomicAdd(&args.seg_tickets[kSegments], 1u) == (unsigned int)args.live_segments - 1u ? 1 : 0;
     }
     __syncthreads();
+    MCB_TRACE(4)
     if (!flag[1]) return;
     // ---- the CTA that completed this shard's last segment ------------------------------------
-    __threadfence();
+    if (args.world > 1) __threadfence_system(); else __threadfence();   // the flags go to other GPUs: system scope
     if (threadIdx.x == 0) args.seg_tickets[kSegments] = 0u;   // ready for the next launch
     if (args.world > 1) {
         if (threadIdx.x < (unsigned)args.n_consumers)
@@ -779,6 +804,7 @@ __device__ __noinline__ void job_tail(const JobArgs &args, const float2 *__restr
         }
     }
     __syncthreads();
+    MCB_TRACE(3)
     const int seg = flag[0];
     if (seg < 0) return;                                    // CTA-uniform: not the last chunk of its segment
     if (seg & 0x100) {
@@ -818,6 +844,7 @@ european_job_kernel(const __grid_constant__ EuropeanParams prm, const __grid_con
     const uint32_t p_lo0 = (uint32_t)base + threadIdx.x;
     const uint64_t left = prm.n_paths - base;
     float sum = 0.0f, sq = 0.0f;
+    MCB_TRACE(0)
     if (left >= (uint64_t)(kSlots * PPS)) {
         uint64_t prod1 = (uint64_t)kPhiloxM1 * p_lo0;
 #pragma unroll 4
@@ -837,9 +864,170 @@ european_job_kernel(const __grid_constant__ EuropeanParams prm, const __grid_con
             }
         }
     }
+    MCB_TRACE(1)
     block_fold2(sum, sq, scratch);
+    MCB_TRACE(2)
     if (threadIdx.x == 0) partials[blockIdx.x] = make_float2(sum, sq);
     job_tail(args, partials, prm.first_chunk, make_float2(sum, sq), dscratch, flag);
+}
+
+// ------------------------------------------------------------------------------------------
+// SMALL jobs (at most kSegments chunks = 1 048 576 paths: the reference's own call sizes, hello.cu:26 / testing.cu).
+// A synchronous call of that size is latency, not throughput: one CTA alone needs 13 750 clk (7 us) for the 64 serial
+// path evaluations of its 256 slots (tools/job_latency_probe.cu).  Here a CLUSTER of eight CTAs on eight SMs prices one
+// chunk: CTA r evaluates paths [8r, 8r + 8) of every slot (eight independent Philox chains per thread) and sends each
+// payoff through distributed shared memory to the CTA that owns the slot -- CTA w sums, in path order, the 32 slots of
+// warp w of the chunk, i.e. exactly the additions slot t of european_kernel performs, then warp_fold's five steps --
+// and the eight warp totals meet in CTA 0 for block_fold2's last three steps.  Same operands, same order, same bits;
+// two cluster barriers instead of 56 more serial path evaluations.  Every chunk of such a job is a segment of its own
+// (no segment ticket, no second look at memory); the tail is warp-level code in the one warp that is left.
+// ------------------------------------------------------------------------------------------
+constexpr int kSmallCluster = 8;                 // CTAs (SMs) per chunk
+constexpr uint64_t kSmallJobChunks = kSegments;  // jobs of at most this many chunks take this kernel
+
+__device__ __forceinline__ uint32_t cluster_cta_rank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_map_shared(const void *p, uint32_t rank)   // my smem address as seen in CTA `rank`
+{
+    uint32_t out;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(out) : "r"((uint32_t)__cvta_generic_to_shared(p)), "r"(rank));
+    return out;
+}
+__device__ __forceinline__ void cluster_store(uint32_t addr, float v)
+{
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+
+// Warp-level tail of european_small_job_kernel (warp 0 of the cluster's CTA 0; lane 0 holds the chunk's totals): store the
+// segment into every consumer's mailbox slot, take the shard ticket, and in the shard's last chunk publish the flag
+// (world > 1) or run the final tree and write the result (world == 1) -- job_publish_segment without block barriers.
+__device__ __forceinline__ void small_job_tail(const JobArgs &args, float2 *__restrict__ partials, uint64_t chunk,
+                                               uint64_t first_chunk, float sum, float sq, int lane)
+{
+    const int slot = (int)(args.epoch % (unsigned long long)kRing);
+    PeerMailbox *mine = args.peers.box[args.rank];
+    const uint32_t n = (uint32_t)args.n_chunks;
+    const double a = (double)sum, b = (double)sq;     // a one-chunk segment IS its partial (see job_tail)
+    int last = 1;
+    if (lane == 0) {
+        partials[chunk - first_chunk] = make_float2(sum, sq);
+        const uint32_t seg = (kSegments * ((uint32_t)chunk + 1u) + n - 1u) / n - 1u;   // n <= kSegments
+        for (int c = 0; c < args.n_consumers; ++c) {
+            if (args.check_acks && args.epoch > (unsigned long long)kRing &&
+                !wait_at_least(&mine->consumed[c], args.epoch - kRing, args.timeout_ns)) {
+                atomicAdd(&mine->timeouts, 1u);
+                continue;
+            }
+            double *dst = args.peers.box[c]->gather[slot] + 2 * seg;
+            __stcg(dst, a);
+            __stcg(dst + 1, b);
+        }
+        if (args.world > 1 || args.live_segments > 1) {
+            if (args.world > 1) __threadfence_system(); else __threadfence();
+            last = atomicAdd(&args.seg_tickets[kSegments], 1u) == (unsigned int)args.live_segments - 1u ? 1 : 0;
+            if (last) args.seg_tickets[kSegments] = 0u;   // ready for the next launch
+        }
+    }
+    last = __shfl_sync(kFullMask, last, 0);
+    MCB_TRACE(4)
+    if (!last) return;
+    if (args.world > 1) {
+        __threadfence_system();
+        if (lane < args.n_consumers)
+            *((volatile unsigned long long *)&args.peers.box[lane]->flags[slot][args.rank]) = args.epoch;
+        return;
+    }
+    if (n == 1) {
+        // the one chunk is segment 63 (lane 31's second operand); every other segment is +0.0 by rule: no memory round trip
+        const double a0 = __shfl_sync(kFullMask, a, 0), b0 = __shfl_sync(kFullMask, b, 0);
+        final_tree_finish(lane == 31 ? 0.0 + a0 : 0.0, lane == 31 ? 0.0 + b0 : 0.0, lane, args.n_paths, args.discount, true,
+                          args.epoch, args.d_out, args.h_out);
+        return;
+    }
+    __threadfence();
+    final_tree_warp(mine->gather[slot], lane, args.n_chunks, args.n_paths, args.discount, true, args.epoch, args.d_out,
+                    args.h_out);
+}
+
+template <int TYPE, int PPS>
+__global__ void __cluster_dims__(kSmallCluster, 1, 1) __launch_bounds__(kSlots)
+european_small_job_kernel(const __grid_constant__ EuropeanParams prm, const __grid_constant__ JobArgs args,
+                          float2 *__restrict__ partials)
+{
+    static_assert(PPS % kSmallCluster == 0 && kWarps == kSmallCluster, "CTA w of the cluster plays warp w of the chunk");
+    constexpr int kPer = PPS / kSmallCluster;            // paths of a slot evaluated by one CTA
+    __shared__ float recv[PPS][32];                      // payoffs of MY 32 slots, by path-in-slot
+    __shared__ float scratch[2 * kWarps];                // CTA 0: the eight warp totals
+    const uint32_t rank = cluster_cta_rank();
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const uint64_t chunk = prm.first_chunk + blockIdx.x / kSmallCluster;
+    const uint64_t base = chunk * (uint64_t)(kSlots * PPS);
+    const uint32_t p_hi = (uint32_t)(base >> 32);
+    const uint32_t p_lo0 = (uint32_t)base + (uint32_t)t;
+    const uint64_t left64 = prm.n_paths - base;
+    const uint32_t left = left64 >= (uint64_t)(kSlots * PPS) ? (uint32_t)(kSlots * PPS) : (uint32_t)left64;
+    // paths of slot t that exist: chunk-local t, t + 256, ... < left
+    const int cnt = (uint32_t)t < left ? (int)((left - (uint32_t)t + kSlots - 1) / kSlots) : 0;
+    MCB_TRACE(0)
+    const uint32_t dst = cluster_map_shared(&recv[rank * kPer][lane], (uint32_t)warp);
+    if (cnt == PPS) {
+        float pay[kPer];
+#pragma unroll
+        for (int j = 0; j < kPer; ++j)
+            pay[j] = european_payoff<TYPE>(p_lo0 + (uint32_t)(((int)rank * kPer + j) * kSlots), p_hi, prm);
+#pragma unroll
+        for (int j = 0; j < kPer; ++j) cluster_store(dst + (uint32_t)(j * 32 * sizeof(float)), pay[j]);
+    } else {
+        for (int j = 0; j < kPer; ++j)
+            if ((int)rank * kPer + j < cnt)
+                cluster_store(dst + (uint32_t)(j * 32 * sizeof(float)),
+                              european_payoff<TYPE>(p_lo0 + (uint32_t)(((int)rank * kPer + j) * kSlots), p_hi, prm));
+    }
+    cluster_arrive();
+    cluster_wait();
+    MCB_TRACE(1)
+    if (warp != 0) return;
+    // ---- warp 0 of CTA `rank` = warp `rank` of the chunk's 256 slots ----
+    const uint32_t slot = rank * 32u + (uint32_t)lane;
+    const int mine = slot < left ? (int)((left - slot + kSlots - 1) / kSlots) : 0;
+    float sum = 0.0f, sq = 0.0f;
+    if (mine == PPS) {
+#pragma unroll 16
+        for (int i = 0; i < PPS; ++i) {
+            const float pay = recv[i][lane];
+            sum = sum + pay;
+            sq = fmaf(pay, pay, sq);
+        }
+    } else {
+        for (int i = 0; i < mine; ++i) {
+            const float pay = recv[i][lane];
+            sum = sum + pay;
+            sq = fmaf(pay, pay, sq);
+        }
+    }
+    sum = warp_fold(sum);
+    sq = warp_fold(sq);
+    if (lane == 0) {
+        cluster_store(cluster_map_shared(&scratch[rank], 0u), sum);
+        cluster_store(cluster_map_shared(&scratch[kWarps + rank], 0u), sq);
+    }
+    cluster_arrive();
+    if (rank != 0) return;
+    cluster_wait();
+    float x = lane < kWarps ? scratch[lane] : 0.0f, y = lane < kWarps ? scratch[kWarps + lane] : 0.0f;
+#pragma unroll
+    for (int off = kWarps / 2; off > 0; off >>= 1) {      // block_fold2's 8 -> 1 step
+        x = x + __shfl_down_sync(kFullMask, x, off);
+        y = y + __shfl_down_sync(kFullMask, y, off);
+    }
+    MCB_TRACE(2)
+    small_job_tail(args, partials, chunk, prm.first_chunk, x, y, lane);
 }
 
 // A shard that owns no chunk of a (small) job still owes its consumers its flag (its segments are

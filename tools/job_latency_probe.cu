@@ -1,0 +1,56 @@
+// job_latency_probe.cu -- where the time of a small synchronous mcb_price_european call goes.  The whole engine is
+// compiled into this probe with MCB_TRACE defined, so thread 0 of CTA 0 stamps clock64() at fixed points of the
+// one-launch job (the stamps cost a few cycles each and are absent from libmcb200.so).
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o tools/job_latency_probe tools/job_latency_probe.cu
+#include <cuda_runtime.h>
+__device__ long long g_trace[16];
+#define MCB_TRACE(i) if (threadIdx.x == 0 && blockIdx.x == 0) g_trace[i] = clock64();
+#include "../monte-carlo-project-cuda_b200/csrc/mcb200.cu"
+
+int main()
+{
+    mcb_engine *e = nullptr;
+    if (mcb_engine_create(0, &e)) { printf("%s\n", mcb_last_error()); return 1; }
+    mcb_option_data opt{};
+    opt.S0 = 100.f; opt.K = 100.f; opt.T = 1.f; opt.r = 0.1f; opt.v = 0.2f; opt.B = 0.f; opt.P1 = 0; opt.P2 = 0; opt.N_PATHS = 0; opt.N_STEPS = 1;
+    const unsigned long long sizes[5] = {1ull, 16384ull, 100000ull, 1000000ull, 2000000ull};
+    // small jobs (european_small_job_kernel): 1 = pricing + first cluster barrier, 2 = slot sums + fold + second barrier
+    const char *names[10] = {"entry", "pricing", "fold", "segment ticket", "shard ticket", "tree loads+fold", "fp64 stats",
+                             "result stores", "", ""};
+    int clk_khz = 0;
+    cudaDeviceGetAttribute(&clk_khz, cudaDevAttrClockRate, 0);
+    for (int k = 0; k < 5; ++k) {
+        mcb_result r;
+        const int reps = 3000;
+        for (int i = 0; i < 300; ++i) mcb_price_european(e, &opt, sizes[k], 1234, MCB_CALL, &r);
+        const auto t0 = std::chrono::steady_clock::now();
+        for (int i = 0; i < reps; ++i) mcb_price_european(e, &opt, sizes[k], 1234, MCB_CALL, &r);
+        const double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count() / reps;
+        cudaDeviceSynchronize();
+        long long t[16];
+        cudaMemcpyFromSymbol(t, g_trace, sizeof(t));
+        printf("%llu paths: %.2f us per call (price %.6f); CTA 0 inside the kernel, cycles since entry (max clock %d MHz):\n",
+               sizes[k], us, r.price, clk_khz / 1000);
+        long long prev = t[0];
+        for (int i = 1; i <= 7; ++i)
+            if (t[i] > t[0]) {
+                printf("   after %-16s %7lld  (+%lld)\n", names[i], t[i] - t[0], t[i] - prev);
+                prev = t[i];
+            }
+        {
+            long long zero[16] = {0};
+            cudaMemcpyToSymbol(g_trace, zero, sizeof(zero));
+        }
+        // host side alone: submit without waiting, then drain
+        uint64_t tk[4];
+        const auto h0 = std::chrono::steady_clock::now();
+        for (int i = 0; i < reps; ++i) {
+            mcb_european_submit(e, &opt, sizes[k], 1234, MCB_CALL, &tk[i & 3]);
+            if ((i & 3) == 3) for (int j = 0; j < 4; ++j) mcb_european_collect(e, tk[j], &r);
+        }
+        printf("   pipelined (4 in flight): %.2f us per call\n",
+               std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - h0).count() / reps);
+    }
+    mcb_engine_destroy(e);
+    return 0;
+}
