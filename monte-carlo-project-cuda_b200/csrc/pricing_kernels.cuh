@@ -879,7 +879,7 @@ european_job_kernel(const __grid_constant__ EuropeanParams prm, const __grid_con
 // payoff through distributed shared memory to the CTA that owns the slot -- CTA w sums, in path order, the 32 slots of
 // warp w of the chunk, i.e. exactly the additions slot t of european_kernel performs, then warp_fold's five steps --
 // and the eight warp totals meet in CTA 0 for block_fold2's last three steps.  Same operands, same order, same bits;
-// two cluster barriers instead of 56 more serial path evaluations.  Every chunk of such a job is a segment of its own
+// two cluster barriers (plus a start-up one hidden behind the pricing) instead of 56 more serial path evaluations.  Every chunk of such a job is a segment of its own
 // (no segment ticket, no second look at memory); the tail is warp-level code in the one warp that is left.
 // ------------------------------------------------------------------------------------------
 constexpr int kSmallCluster = 8;                 // CTAs (SMs) per chunk
@@ -975,20 +975,31 @@ european_small_job_kernel(const __grid_constant__ EuropeanParams prm, const __gr
     // paths of slot t that exist: chunk-local t, t + 256, ... < left
     const int cnt = (uint32_t)t < left ? (int)((left - (uint32_t)t + kSlots - 1) / kSlots) : 0;
     MCB_TRACE(0)
+    // "every CTA of the cluster has started" (a CTA's shared memory may only be written by its peers from then on):
+    // arrive now, wait just before the first remote store -- the pricing in between hides the barrier
+#ifndef MCB_NO_START_BARRIER              // (tools/job_latency_probe.cu measures what it costs)
+    cluster_arrive();
+#endif
     const uint32_t dst = cluster_map_shared(&recv[rank * kPer][lane], (uint32_t)warp);
+    float pay[kPer] = {};
     if (cnt == PPS) {
-        float pay[kPer];
 #pragma unroll
         for (int j = 0; j < kPer; ++j)
             pay[j] = european_payoff<TYPE>(p_lo0 + (uint32_t)(((int)rank * kPer + j) * kSlots), p_hi, prm);
-#pragma unroll
-        for (int j = 0; j < kPer; ++j) cluster_store(dst + (uint32_t)(j * 32 * sizeof(float)), pay[j]);
     } else {
+#pragma unroll
         for (int j = 0; j < kPer; ++j)
             if ((int)rank * kPer + j < cnt)
-                cluster_store(dst + (uint32_t)(j * 32 * sizeof(float)),
-                              european_payoff<TYPE>(p_lo0 + (uint32_t)(((int)rank * kPer + j) * kSlots), p_hi, prm));
+                pay[j] = european_payoff<TYPE>(p_lo0 + (uint32_t)(((int)rank * kPer + j) * kSlots), p_hi, prm);
     }
+    __syncwarp();                         // .aligned barriers need all 32 lanes together
+#ifndef MCB_NO_START_BARRIER
+    cluster_wait();
+#endif
+#pragma unroll
+    for (int j = 0; j < kPer; ++j)
+        if ((int)rank * kPer + j < cnt) cluster_store(dst + (uint32_t)(j * 32 * sizeof(float)), pay[j]);
+    __syncwarp();
     cluster_arrive();
     cluster_wait();
     MCB_TRACE(1)
@@ -1017,6 +1028,7 @@ european_small_job_kernel(const __grid_constant__ EuropeanParams prm, const __gr
         cluster_store(cluster_map_shared(&scratch[rank], 0u), sum);
         cluster_store(cluster_map_shared(&scratch[kWarps + rank], 0u), sq);
     }
+    __syncwarp();
     cluster_arrive();
     if (rank != 0) return;
     cluster_wait();

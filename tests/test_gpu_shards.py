@@ -42,20 +42,25 @@ def multi_engines(pkg):
 
 def test_single_engine_prices_in_one_launch(pkg, engine, orc):
     """mcb_price_european = ONE kernel launch: pricing, segment folds, final tree and the host-visible
-    result all come from european_job_kernel (the reference: two launches, a sync and a copy,
-    inc/wrappers.cuh:41-49)."""
-    for n in (1, 255, 100_000, pkg.EUROPEAN_CHUNK, 64 * pkg.EUROPEAN_CHUNK, 200 * pkg.EUROPEAN_CHUNK + 999):
+    result all come from european_small_job_kernel (jobs of at most 64 chunks: a cluster of eight CTAs per
+    chunk) or european_job_kernel (the reference: two launches, a sync and a copy, inc/wrappers.cuh:41-49).
+    The sizes walk the cluster kernel's edges: one lane, one warp +- 1, one slot row +- 1, half a chunk, a
+    chunk +- 1, ragged multi-chunk jobs, the largest small job and the first job past it."""
+    C = pkg.EUROPEAN_CHUNK
+    for i, n in enumerate((1, 2, 31, 32, 33, 255, 256, 257, 2047, 2048, 2049, 8191, C - 1, C, C + 1, 3 * C + 5, 100_000,
+                           1_000_000, 64 * C - 1, 64 * C, 64 * C + 1, 200 * C + 999)):
         opt = pkg.option(N_PATHS=n)
+        typ = pkg.PUT if i % 3 == 2 else pkg.CALL
         before = engine.launch_count
-        res = engine.price_european(opt, n, 1234, pkg.CALL)
+        res = engine.price_european(opt, n, 1234, typ)
         assert engine.launch_count - before == 1
         # the segments the kernel left in mapped host memory fold to the result with the oracle's tree
         seg = engine.last_segments()
         s, q = orc.final_tree_f64(seg)
         assert s == res.sum and q == res.sumsq and res.n_paths == n
         # ... and are the oracle's segment tree of the kernel's own chunk partials
-        cp = engine.european_chunk_partials(opt, n, 1234, pkg.CALL)
-        assert (orc.segment_tree_f64(cp) == seg).all()
+        cp = engine.european_chunk_partials(opt, n, 1234, typ)
+        assert (orc.segment_tree_f64(cp) == seg).all(), n
 
 
 def test_large_shards_take_the_two_launch_route_with_the_same_bits(pkg, engine, multi_engines):
