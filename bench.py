@@ -36,6 +36,7 @@ import argparse
 import json
 import math
 import os
+import subprocess
 import sys
 import threading
 import time
@@ -619,15 +620,32 @@ def other_workloads(torch, pkg, eng, hbm_gbs, peak_src):
     # (host in / host out): call latency.  ONE launch, result through mapped pinned memory.
     for label, npaths in (("european_1e6_sync_call", 1_000_000), ("european_1e5_sync_call_hello_cu_size", 100_000)):
         o0 = pkg.option(N_PATHS=npaths, **CFG)
-        for _ in range(20):
-            r0 = eng.price_european(o0, 0, SEED, pkg.CALL)
-        t0 = time.perf_counter()
         for _ in range(500):
             r0 = eng.price_european(o0, 0, SEED, pkg.CALL)
-        dt0 = (time.perf_counter() - t0) / 500
+        t0 = time.perf_counter()
+        for _ in range(2000):
+            r0 = eng.price_european(o0, 0, SEED, pkg.CALL)
+        dt0 = (time.perf_counter() - t0) / 2000
         out[label] = {"us_per_call": 1e6 * dt0, "paths_per_s": npaths / dt0, "price": r0.price,
                       "std_error": r0.std_error, "closed_form": bs_call(**CFG),
-                      "z_score": (r0.price - bs_call(**CFG)) / r0.std_error, "launches_per_call": 1}
+                      "z_score": (r0.price - bs_call(**CFG)) / r0.std_error, "launches_per_call": 1,
+                      "note": "through the Python binding (ctypes adds ~2 us per call); the same call from C is "
+                              "c_abi_sync_call_us below"}
+    # the same synchronous call from plain C (examples/price_c.c, built by build()): no interpreter in the loop
+    exe = os.path.join(os.path.dirname(os.path.abspath(__file__)), "build", "price_c")
+    if os.path.exists(exe):
+        try:
+            txt = subprocess.run([exe, str(torch.cuda.current_device())], capture_output=True, text=True, timeout=120).stdout
+            lat = {}
+            for line in txt.splitlines():
+                if line.startswith("C_LAT"):
+                    key, us = line.split("mcb_price_european(")[1].split(" paths")[0], float(line.split(": ")[1].split(" us")[0])
+                    lat[key] = min(us, lat.get(key, us))     # (the small sizes are timed twice: the better window)
+            if lat:
+                out["c_abi_sync_call_us"] = {"paths_to_us": lat, "launches_per_call": 1,
+                                             "what": "mcb_price_european from C99 (examples/price_c.c), host in / host out"}
+        except Exception as exc:   # a missing example binary must not take the bench line down
+            out["c_abi_sync_call_us"] = {"error": repr(exc)}
 
     # the optional second keying of SURVEY 8(d): path p <-> normal p & 3 of subsequence p >> 2 (four paths per Philox
     # block).  Reported separately; the headline above is the canonical keying.

@@ -69,12 +69,13 @@ int main(int argc, char **argv)
     /* latency of the synchronous call, from the reference's own job size (hello.cu:13: 1e5 paths) down to
      * one path (pure call overhead: launch + ticket + final tree + host-visible result) */
     {
-        const uint64_t sizes[4] = {1, 16384, 100000, 1000000};
-        for (int k = 0; k < 4; ++k) {
+        const uint64_t sizes[6] = {1, 16384, 100000, 1000000, 16384, 1};   /* (the small ones twice: first and last) */
+        for (int k = 0; k < 6; ++k) {
             struct timespec t0, t1;
             mcb_result r;
             const int reps = 2000;
-            for (int i = 0; i < 50; ++i) rc |= mcb_price_european(engine, &opt, sizes[k], 1234, MCB_CALL, &r);
+            for (int i = 0; i < (k ? 500 : 5000); ++i)   /* (the first size also lets the clocks settle) */
+                rc |= mcb_price_european(engine, &opt, sizes[k], 1234, MCB_CALL, &r);
             clock_gettime(CLOCK_MONOTONIC, &t0);
             for (int i = 0; i < reps; ++i) rc |= mcb_price_european(engine, &opt, sizes[k], 1234, MCB_CALL, &r);
             clock_gettime(CLOCK_MONOTONIC, &t1);

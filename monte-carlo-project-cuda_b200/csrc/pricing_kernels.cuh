@@ -601,6 +601,9 @@ segment_sets_kernel(const float2 *__restrict__ partials, uint64_t partials_strid
 #ifndef MCB_TRACE                 // tools/job_latency_probe.cu defines it to stamp clock64() along the one-CTA job
 #define MCB_TRACE(i)
 #endif
+#ifndef MCB_TRACE_CTA             // ... and to stamp %globaltimer in every CTA of the small-job kernel
+#define MCB_TRACE_CTA(i)
+#endif
 constexpr int kMaxPeers = 16;  // MCB_MAX_PEERS
 constexpr int kRing = 4;       // MCB_PIPELINE_DEPTH: mailbox slots = jobs in flight per engine
 
@@ -609,6 +612,9 @@ struct PeerMailbox {           // one per shard, in that shard's HBM; written by
     unsigned long long flags[kRing][kMaxPeers];        // flags[slot][r] = last epoch producer r published there
     unsigned long long consumed[kMaxPeers];            // consumed[c] = last epoch consumer c folded (its ack to ME)
     unsigned int timeouts;                             // bounded waits that ran out (sticky, diagnostic)
+    // small one-GPU jobs: the segments as self-tagged words (low half | tag << 32, high half | tag << 32 of sum and
+    // sumsq), so that no fence and no ticket stand between a chunk's totals and the final tree (small_job_tail)
+    alignas(32) unsigned long long tagged[kRing][kSegments][4];   // (read with 16-byte loads)
 };
 struct PeerTable {
     PeerMailbox *box[kMaxPeers];                       // box[r] = shard r's mailbox as mapped here
@@ -878,9 +884,10 @@ european_job_kernel(const __grid_constant__ EuropeanParams prm, const __grid_con
 // chunk: CTA r evaluates paths [8r, 8r + 8) of every slot (eight independent Philox chains per thread) and sends each
 // payoff through distributed shared memory to the CTA that owns the slot -- CTA w sums, in path order, the 32 slots of
 // warp w of the chunk, i.e. exactly the additions slot t of european_kernel performs, then warp_fold's five steps --
-// and the eight warp totals meet in CTA 0 for block_fold2's last three steps.  Same operands, same order, same bits;
-// two cluster barriers (plus a start-up one hidden behind the pricing) instead of 56 more serial path evaluations.  Every chunk of such a job is a segment of its own
-// (no segment ticket, no second look at memory); the tail is warp-level code in the one warp that is left.
+// and the eight warp totals meet in CTA 0 for block_fold2's last three steps.  Same operands, same order, same bits.
+// Both hand-offs are st.async stores that signal an mbarrier in the RECEIVER's shared memory (no fence, no cluster
+// barrier on the data path; the one cluster barrier, "everybody has started", hides behind the pricing).  Every chunk
+// of such a job is a segment of its own (no segment ticket); the tail is warp-level code in the one warp that is left.
 // ------------------------------------------------------------------------------------------
 constexpr int kSmallCluster = 8;                 // CTAs (SMs) per chunk
 constexpr uint64_t kSmallJobChunks = kSegments;  // jobs of at most this many chunks take this kernel
@@ -897,16 +904,44 @@ __device__ __forceinline__ uint32_t cluster_map_shared(const void *p, uint32_t r
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(out) : "r"((uint32_t)__cvta_generic_to_shared(p)), "r"(rank));
     return out;
 }
-__device__ __forceinline__ void cluster_store(uint32_t addr, float v)
-{
-    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
-}
-__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+// An mbarrier in MY shared memory that remote st.async stores signal: the receiver learns that the bytes it expects have
+// landed without any fence on the sender's side (a barrier.cluster.arrive.release costs a MEMBAR.ALL.GPU: ~0.5 us).
+__device__ __forceinline__ void mbar_init_expect(unsigned long long *bar, uint32_t bytes)
+{
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(a) : "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar)   // first phase
+{
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+    uint32_t done;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], 0;\n"
+                     " selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done)
+                     : "r"(a)
+                     : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void cluster_store_signal(uint32_t addr, float v, uint32_t bar)   // both in the same remote CTA
+{
+    asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(addr),
+                 "r"(__float_as_uint(v)), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void cluster_store_signal2(uint32_t addr, float v, float w, uint32_t bar)
+{
+    asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];" ::"r"(addr),
+                 "r"(__float_as_uint(v)), "r"(__float_as_uint(w)), "r"(bar)
+                 : "memory");
+}
 
-// Warp-level tail of european_small_job_kernel (warp 0 of the cluster's CTA 0; lane 0 holds the chunk's totals): store the
-// segment into every consumer's mailbox slot, take the shard ticket, and in the shard's last chunk publish the flag
-// (world > 1) or run the final tree and write the result (world == 1) -- job_publish_segment without block barriers.
+// Warp-level tail of european_small_job_kernel in a group of several shards (warp 0 of the cluster's CTA 0; lane 0 holds
+// the chunk's totals): store the segment into every consumer's mailbox slot, take the shard ticket, and in the shard's
+// last chunk publish the flag -- job_publish_segment without block barriers.
 __device__ __forceinline__ void small_job_tail(const JobArgs &args, float2 *__restrict__ partials, uint64_t chunk,
                                                uint64_t first_chunk, float sum, float sq, int lane)
 {
@@ -928,31 +963,97 @@ __device__ __forceinline__ void small_job_tail(const JobArgs &args, float2 *__re
             __stcg(dst, a);
             __stcg(dst + 1, b);
         }
-        if (args.world > 1 || args.live_segments > 1) {
-            if (args.world > 1) __threadfence_system(); else __threadfence();
-            last = atomicAdd(&args.seg_tickets[kSegments], 1u) == (unsigned int)args.live_segments - 1u ? 1 : 0;
-            if (last) args.seg_tickets[kSegments] = 0u;   // ready for the next launch
-        }
+        __threadfence_system();
+        last = atomicAdd(&args.seg_tickets[kSegments], 1u) == (unsigned int)args.live_segments - 1u ? 1 : 0;
+        if (last) args.seg_tickets[kSegments] = 0u;   // ready for the next launch
     }
     last = __shfl_sync(kFullMask, last, 0);
-    MCB_TRACE(4)
     if (!last) return;
-    if (args.world > 1) {
-        __threadfence_system();
-        if (lane < args.n_consumers)
-            *((volatile unsigned long long *)&args.peers.box[lane]->flags[slot][args.rank]) = args.epoch;
-        return;
+    __threadfence_system();
+    if (lane < args.n_consumers)
+        *((volatile unsigned long long *)&args.peers.box[lane]->flags[slot][args.rank]) = args.epoch;
+}
+
+// Spin (bounded) until the tagged words of this lane's two segments (each only if `want`ed) carry `tag`; the loads of
+// both segments are in flight together, so the usual case costs one L2 round trip.  Returns the doubles they spell.
+__device__ __forceinline__ bool read_tagged_pair(const unsigned long long *lo, const unsigned long long *hi, bool want_lo,
+                                                 bool want_hi, unsigned long long tag, unsigned long long timeout_ns,
+                                                 double &lo_a, double &lo_b, double &hi_a, double &hi_b)
+{
+    unsigned long long t0 = 0;
+    while (want_lo || want_hi) {
+        unsigned long long x[4] = {0, 0, 0, 0}, y[4] = {0, 0, 0, 0};
+        if (want_lo) {
+            asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(x[0]), "=l"(x[1]) : "l"(lo));
+            asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(x[2]), "=l"(x[3]) : "l"(lo + 2));
+        }
+        if (want_hi) {
+            asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(y[0]), "=l"(y[1]) : "l"(hi));
+            asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(y[2]), "=l"(y[3]) : "l"(hi + 2));
+        }
+        if (want_lo && (x[0] >> 32) == tag && (x[1] >> 32) == tag && (x[2] >> 32) == tag && (x[3] >> 32) == tag) {
+            lo_a = __longlong_as_double((long long)((x[0] & 0xffffffffull) | (x[1] << 32)));
+            lo_b = __longlong_as_double((long long)((x[2] & 0xffffffffull) | (x[3] << 32)));
+            want_lo = false;
+        }
+        if (want_hi && (y[0] >> 32) == tag && (y[1] >> 32) == tag && (y[2] >> 32) == tag && (y[3] >> 32) == tag) {
+            hi_a = __longlong_as_double((long long)((y[0] & 0xffffffffull) | (y[1] << 32)));
+            hi_b = __longlong_as_double((long long)((y[2] & 0xffffffffull) | (y[3] << 32)));
+            want_hi = false;
+        }
+        if (want_lo || want_hi) {
+            if (t0 == 0) t0 = global_timer_ns();
+            else if (global_timer_ns() - t0 > timeout_ns) return false;
+        }
     }
+    return true;
+}
+
+// world == 1 version of the tail.  One chunk: the tree runs on registers.  2..64 chunks: every chunk's lane 0 stores
+// its segment as four self-tagged 8-byte words and leaves; warp 0 of chunk 0 -- the first cluster to be scheduled,
+// so it is waiting while the others still price -- reads the live segments until their tags match (bounded by the
+// engine's timeout; the other chunks wait for nobody, so they always get their SMs) and runs the tree.  Neither a
+// fence nor an atomic round trip is left on the path from the last payoff to the result (they cost 2 400 + 1 100
+// clk, tools/job_latency_probe.cu); the plain copy in `gather` serves mcb_last_segments.
+__device__ __forceinline__ void small_job_tail_one_gpu(const JobArgs &args, float2 *__restrict__ partials, uint64_t chunk,
+                                                       float sum, float sq, int lane)
+{
+    const int slot = (int)(args.epoch % (unsigned long long)kRing);
+    PeerMailbox *mine = args.peers.box[0];
+    const uint32_t n = (uint32_t)args.n_chunks;
+    const double a = (double)sum, b = (double)sq;     // a one-chunk segment IS its partial (see job_tail)
+    const unsigned long long tag = args.epoch & 0xffffffffull;
+    if (lane == 0) {
+        partials[chunk] = make_float2(sum, sq);
+        const uint32_t seg = (kSegments * ((uint32_t)chunk + 1u) + n - 1u) / n - 1u;   // n <= kSegments
+        double *dst = mine->gather[slot] + 2 * seg;
+        dst[0] = a;
+        dst[1] = b;
+        if (n > 1) {
+            const unsigned long long ua = (unsigned long long)__double_as_longlong(a), ub = (unsigned long long)__double_as_longlong(b);
+            volatile unsigned long long *w = mine->tagged[slot][seg];
+            w[0] = (tag << 32) | (ua & 0xffffffffull);
+            w[1] = (tag << 32) | (ua >> 32);
+            w[2] = (tag << 32) | (ub & 0xffffffffull);
+            w[3] = (tag << 32) | (ub >> 32);
+        }
+    }
+    MCB_TRACE(4)
     if (n == 1) {
-        // the one chunk is segment 63 (lane 31's second operand); every other segment is +0.0 by rule: no memory round trip
+        // the one chunk is segment 63 (lane 31's second operand); every other segment is +0.0 by rule
         const double a0 = __shfl_sync(kFullMask, a, 0), b0 = __shfl_sync(kFullMask, b, 0);
         final_tree_finish(lane == 31 ? 0.0 + a0 : 0.0, lane == 31 ? 0.0 + b0 : 0.0, lane, args.n_paths, args.discount, true,
                           args.epoch, args.d_out, args.h_out);
         return;
     }
-    __threadfence();
-    final_tree_warp(mine->gather[slot], lane, args.n_chunks, args.n_paths, args.discount, true, args.epoch, args.d_out,
-                    args.h_out);
+    if (chunk != 0) return;
+    double lo_a = 0.0, lo_b = 0.0, hi_a = 0.0, hi_b = 0.0;
+    bool ok = read_tagged_pair(mine->tagged[slot][lane], mine->tagged[slot][lane + 32], !segment_is_empty(args.n_chunks, lane),
+                               !segment_is_empty(args.n_chunks, lane + 32), tag, args.timeout_ns, lo_a, lo_b, hi_a, hi_b);
+    __syncwarp();
+    if (!ok) atomicAdd(&mine->timeouts, 1u);
+    ok = __all_sync(kFullMask, ok);
+    final_tree_finish(lo_a + hi_a, lo_b + hi_b, lane, args.n_paths, args.discount, ok, args.epoch, args.d_out, args.h_out);
 }
 
 template <int TYPE, int PPS>
@@ -963,7 +1064,8 @@ european_small_job_kernel(const __grid_constant__ EuropeanParams prm, const __gr
     static_assert(PPS % kSmallCluster == 0 && kWarps == kSmallCluster, "CTA w of the cluster plays warp w of the chunk");
     constexpr int kPer = PPS / kSmallCluster;            // paths of a slot evaluated by one CTA
     __shared__ float recv[PPS][32];                      // payoffs of MY 32 slots, by path-in-slot
-    __shared__ float scratch[2 * kWarps];                // CTA 0: the eight warp totals
+    __shared__ float2 totals[kWarps];                    // CTA 0: the eight warp totals
+    __shared__ alignas(8) unsigned long long bars[2];    // [0] my slots' payoffs have landed, [1] (CTA 0) the eight totals have
     const uint32_t rank = cluster_cta_rank();
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const uint64_t chunk = prm.first_chunk + blockIdx.x / kSmallCluster;
@@ -974,13 +1076,23 @@ european_small_job_kernel(const __grid_constant__ EuropeanParams prm, const __gr
     const uint32_t left = left64 >= (uint64_t)(kSlots * PPS) ? (uint32_t)(kSlots * PPS) : (uint32_t)left64;
     // paths of slot t that exist: chunk-local t, t + 256, ... < left
     const int cnt = (uint32_t)t < left ? (int)((left - (uint32_t)t + kSlots - 1) / kSlots) : 0;
+    // ... and of the slot whose payoffs lane `lane` of warp 0 will sum here (slot 32 rank + lane)
+    const uint32_t slot = rank * 32u + (uint32_t)lane;
+    const int mine = slot < left ? (int)((left - slot + kSlots - 1) / kSlots) : 0;
     MCB_TRACE(0)
-    // "every CTA of the cluster has started" (a CTA's shared memory may only be written by its peers from then on):
-    // arrive now, wait just before the first remote store -- the pricing in between hides the barrier
-#ifndef MCB_NO_START_BARRIER              // (tools/job_latency_probe.cu measures what it costs)
-    cluster_arrive();
-#endif
-    const uint32_t dst = cluster_map_shared(&recv[rank * kPer][lane], (uint32_t)warp);
+    MCB_TRACE_CTA(0)
+    if (warp == 0) {
+        const uint32_t expected = __reduce_add_sync(kFullMask, (uint32_t)mine) * (uint32_t)sizeof(float);
+        if (lane == 0) {
+            mbar_init_expect(&bars[0], expected);
+            mbar_init_expect(&bars[1], (uint32_t)(kWarps * sizeof(float2)));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+    }
+    // "every CTA of the cluster has started and its barriers exist" (a CTA's shared memory may only be written by its
+    // peers from then on): arrive now, wait just before the first remote store -- the pricing in between hides it
+    cluster_arrive_relaxed();
     float pay[kPer] = {};
     if (cnt == PPS) {
 #pragma unroll
@@ -993,20 +1105,20 @@ european_small_job_kernel(const __grid_constant__ EuropeanParams prm, const __gr
                 pay[j] = european_payoff<TYPE>(p_lo0 + (uint32_t)(((int)rank * kPer + j) * kSlots), p_hi, prm);
     }
     __syncwarp();                         // .aligned barriers need all 32 lanes together
-#ifndef MCB_NO_START_BARRIER
     cluster_wait();
-#endif
+    {
+        const uint32_t dst = cluster_map_shared(&recv[rank * kPer][lane], (uint32_t)warp);
+        const uint32_t bar = cluster_map_shared(&bars[0], (uint32_t)warp);
 #pragma unroll
-    for (int j = 0; j < kPer; ++j)
-        if ((int)rank * kPer + j < cnt) cluster_store(dst + (uint32_t)(j * 32 * sizeof(float)), pay[j]);
-    __syncwarp();
-    cluster_arrive();
-    cluster_wait();
-    MCB_TRACE(1)
+        for (int j = 0; j < kPer; ++j)
+            if ((int)rank * kPer + j < cnt) cluster_store_signal(dst + (uint32_t)(j * 32 * sizeof(float)), pay[j], bar);
+    }
+    MCB_TRACE_CTA(1)
     if (warp != 0) return;
     // ---- warp 0 of CTA `rank` = warp `rank` of the chunk's 256 slots ----
-    const uint32_t slot = rank * 32u + (uint32_t)lane;
-    const int mine = slot < left ? (int)((left - slot + kSlots - 1) / kSlots) : 0;
+    mbar_wait(&bars[0]);
+    MCB_TRACE(1)
+    MCB_TRACE_CTA(2)
     float sum = 0.0f, sq = 0.0f;
     if (mine == PPS) {
 #pragma unroll 16
@@ -1024,22 +1136,19 @@ european_small_job_kernel(const __grid_constant__ EuropeanParams prm, const __gr
     }
     sum = warp_fold(sum);
     sq = warp_fold(sq);
-    if (lane == 0) {
-        cluster_store(cluster_map_shared(&scratch[rank], 0u), sum);
-        cluster_store(cluster_map_shared(&scratch[kWarps + rank], 0u), sq);
-    }
-    __syncwarp();
-    cluster_arrive();
+    if (lane == 0) cluster_store_signal2(cluster_map_shared(&totals[rank], 0u), sum, sq, cluster_map_shared(&bars[1], 0u));
+    MCB_TRACE_CTA(3)
     if (rank != 0) return;
-    cluster_wait();
-    float x = lane < kWarps ? scratch[lane] : 0.0f, y = lane < kWarps ? scratch[kWarps + lane] : 0.0f;
+    mbar_wait(&bars[1]);
+    float x = lane < kWarps ? totals[lane].x : 0.0f, y = lane < kWarps ? totals[lane].y : 0.0f;
 #pragma unroll
     for (int off = kWarps / 2; off > 0; off >>= 1) {      // block_fold2's 8 -> 1 step
         x = x + __shfl_down_sync(kFullMask, x, off);
         y = y + __shfl_down_sync(kFullMask, y, off);
     }
     MCB_TRACE(2)
-    small_job_tail(args, partials, chunk, prm.first_chunk, x, y, lane);
+    if (args.world == 1) small_job_tail_one_gpu(args, partials, chunk, x, y, lane);
+    else small_job_tail(args, partials, chunk, prm.first_chunk, x, y, lane);
 }
 
 // A shard that owns no chunk of a (small) job still owes its consumers its flag (its segments are

@@ -5,6 +5,13 @@
 #include <cuda_runtime.h>
 __device__ long long g_trace[16];
 #define MCB_TRACE(i) if (threadIdx.x == 0 && blockIdx.x == 0) g_trace[i] = clock64();
+__device__ unsigned long long g_cta[4][512];   // [stamp][CTA]: entry, payoffs sent, first barrier passed, slot sums done
+#define MCB_TRACE_CTA(i)                                                              \
+    if (threadIdx.x == 0) {                                                           \
+        unsigned long long now;                                                       \
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));                       \
+        g_cta[i][blockIdx.x] = now;                                                   \
+    }
 #include "../monte-carlo-project-cuda_b200/csrc/mcb200.cu"
 
 int main()
@@ -40,6 +47,23 @@ int main()
         {
             long long zero[16] = {0};
             cudaMemcpyToSymbol(g_trace, zero, sizeof(zero));
+        }
+        if (sizes[k] <= 1000000ull) {
+            static unsigned long long c[4][512];
+            cudaMemcpyFromSymbol(c, g_cta, sizeof(c));
+            const int n_cta = (int)((sizes[k] + 16383) / 16384) * 8;
+            unsigned long long first = ~0ull;
+            for (int i = 0; i < n_cta; ++i) first = c[0][i] < first ? c[0][i] : first;
+            const char *what[4] = {"entry", "payoffs sent", "first barrier passed", "slot sums done"};
+            for (int st = 0; st < 4; ++st) {
+                unsigned long long lo = ~0ull, hi = 0, sum = 0;
+                for (int i = 0; i < n_cta; ++i) {
+                    const unsigned long long v = c[st][i] - first;
+                    lo = v < lo ? v : lo; hi = v > hi ? v : hi; sum += v;
+                }
+                printf("   all %d CTAs, ns after the first entry: %-22s min %5llu  mean %5llu  max %5llu\n", n_cta, what[st], lo,
+                       sum / n_cta, hi);
+            }
         }
         // host side alone: submit without waiting, then drain
         uint64_t tk[4];
