@@ -14,6 +14,7 @@ LIB = os.path.join(ROOT, "monte-carlo-project-cuda_b200", "libmcb200.so")
 KERNELS = {   # label -> substring of the mangled name
     "european_kernel": "european_kernelILi0ELi64ELi4E",
     "european_job_kernel": "european_job_kernelILi0ELi64E",
+    "european_small_job_kernel": "european_small_job_kernelILi0ELi64E",
     "european_packed_kernel": "european_packed_kernelILi0ELi64E",
     "trajectory_long_kernel_prices_counts": "trajectory_long_kernelILb1ELb0ELi4E",
     "bullet_kernel": "bullet_kernelILi4E",
@@ -74,7 +75,7 @@ def main():
             out += ["", f"-- hottest loop body 0x{best[1]:x}..0x{best[2]:x} ({len(best[3])} instructions) --"]
             out += [f"{c:6d} {op}" for op, c in hist.most_common()]
         marks = [k for k in ("UBLKCP", "UTMASTG", "UTMACMDFLUSH", "FFMA2", "FADD2", "FMUL2", "UIMAD.WIDE", "REDG", "ATOMG",
-                             "MEMBAR", "ST.E", "STG") if any(k in t for _, t in ins)]
+                             "MEMBAR", "ST.E", "STG", "STAS", "SYNCS.PHASECHK", "UCGABAR") if any(k in t for _, t in ins)]
         out += ["", "markers present: " + (", ".join(marks) or "none")]
         with open(os.path.join(ROOT, "profiles", f"r2_sass_hist_{label}.txt"), "w") as f:
             f.write("\n".join(out) + "\n")
