@@ -842,17 +842,18 @@ void host_slot_expire(HostSlot *hs, unsigned long long epoch)
 }
 
 // One shard's launch of job `epoch`: european_job_kernel over the chunks it owns (or the publish-only
-// kernel when it owns none), on the shard's main stream.
+// kernel when it owns none), on the shard's main stream.  solo: the leader of an in-process group prices the whole
+// (small) job by itself, as a group of one -- the tree does not depend on the sharding, so the bits are the same.
 int submit_shard(mcb_engine *s, mcb_engine *L, const mcb_option_data *opt, uint64_t n_paths, uint64_t seed,
-                 int option_type, unsigned long long epoch)
+                 int option_type, unsigned long long epoch, bool solo = false)
 {
     DeviceGuard g(s->device);
     if (!g.ok) return fail(MCB_ERR_CUDA, "cudaSetDevice(%d) failed", s->device);
-    const int rank = s->rank, world = s->world;
+    const int rank = solo ? 0 : s->rank, world = solo ? 1 : s->world;
     const int slot = (int)(epoch % kRing);
     // groups of several shards alternate their jobs between two pricing streams: the next job's CTAs
     // take the SM slots this job's last wave, segment launch and event records leave idle
-    const int lane = (world > 1) ? (int)(epoch & 1ull) : 0;
+    const int lane = (s->world > 1) ? (int)(epoch & 1ull) : 0;
     cudaStream_t st = lane ? s->stream2 : s->stream;
     DeviceBuffer<float2> &partials = lane ? s->partials2 : s->partials;
     const uint64_t n_chunks = (n_paths + kEuropeanChunk - 1) / kEuropeanChunk;
@@ -884,8 +885,8 @@ int submit_shard(mcb_engine *s, mcb_engine *L, const mcb_option_data *opt, uint6
             ++args.live_segments;
     args.rank = rank;
     args.world = world;
-    args.n_consumers = s->ipc ? world : 1;
-    args.check_acks = s->ipc ? 1 : 0;
+    args.n_consumers = (s->ipc && !solo) ? world : 1;
+    args.check_acks = (s->ipc && !solo) ? 1 : 0;
     if (world == 1) {
         args.d_out = s->results.ptr;
         args.h_out = &s->h_ring[epoch % kHostRing];
@@ -921,6 +922,9 @@ int submit_shard(mcb_engine *s, mcb_engine *L, const mcb_option_data *opt, uint6
     s->launches++;
     CU(cudaGetLastError());
     if (world > 1) CU(cudaEventRecord(s->p_done[slot], st));
+    // a solo job used the leader's mailbox slot: the producers of job epoch + kRing wait for this event as they
+    // would for the final pass of a sharded job
+    if (solo) CU(cudaEventRecord(L->f_done[slot], st));
     return MCB_OK;
 }
 
@@ -947,6 +951,10 @@ int mcb_european_submit(mcb_engine *e, const mcb_option_data *opt, uint64_t n_pa
     e->ring_chunks[epoch % kHostRing] = (n_paths + kEuropeanChunk - 1) / kEuropeanChunk;
     std::atomic_thread_fence(std::memory_order_seq_cst);
     const size_t n = shard_count(e);
+    // A small job on an in-process group is not worth sharding (a 10^5-path call is 10 us on one GPU, 30-40 us once
+    // launcher threads, cross-device events and a final pass are involved): the leader prices it alone, same bits.
+    if (n > 1 && e->in_process && e->small_jobs && e->ring_chunks[epoch % kHostRing] <= kSmallJobChunks)
+        return submit_shard(e, e, opt, n_paths, seed, option_type, epoch, true);
     // the other shards' launcher threads enqueue their devices while this thread does the leader's
     for (size_t i = 1; i < n; ++i) {
         mcb_engine *s = shard_at(e, i);

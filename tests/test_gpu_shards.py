@@ -91,20 +91,24 @@ def test_large_shards_take_the_two_launch_route_with_the_same_bits(pkg, engine, 
 
 
 def test_multi_engine_european_bits(pkg, engine, multi_engines):
-    sizes = (100_000,                                   # 7 chunks: most shards own nothing, most segments are empty
-             63 * pkg.EUROPEAN_CHUNK + 5,               # fewer chunks than segments
+    """Jobs of at most 64 chunks are priced by the group's leader alone (ONE launch: sharding a 10 us job costs more
+    than it saves, and the tree does not depend on the sharding); larger ones by every shard + the final pass."""
+    sizes = (1, 100_000,                                # small: the leader alone
+             63 * pkg.EUROPEAN_CHUNK + 5, 64 * pkg.EUROPEAN_CHUNK,
+             64 * pkg.EUROPEAN_CHUNK + 1,               # 65 chunks: most shards own one or two segments' worth
              200 * pkg.EUROPEAN_CHUNK + 999,            # >= 64 chunks, ragged tail
              1 << 24)
     for multi in multi_engines:
         k = multi.shard_count
         assert k == len(multi.devices)
-        for rep in range(3):                            # 3 x 8 jobs: the 4-slot mailbox ring wraps several times
+        for rep in range(3):                            # 3 x 14 jobs, small and sharded interleaved: the ring wraps
             for n in sizes:
                 for typ in (pkg.CALL, pkg.PUT):
                     opt = pkg.option(N_PATHS=n, K=100.0 + rep)
                     before = multi.launch_count
                     got = multi.price_european(opt, n, 1234 + rep, typ)
-                    assert multi.launch_count - before == k + 1   # one launch per shard + the final pass
+                    small = -(-n // pkg.EUROPEAN_CHUNK) <= 64
+                    assert multi.launch_count - before == (1 if small else k + 1)   # one per shard + the final pass
                     want = engine.price_european(opt, n, 1234 + rep, typ)
                     assert _bits(got) == _bits(want), (multi.devices, n, typ, got, want)
         assert multi.peer_timeouts() == 0

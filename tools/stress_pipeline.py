@@ -19,8 +19,10 @@ pkg = entry.load_package()
 jobs = int(sys.argv[1]) if len(sys.argv) > 1 else 4000
 INPROC = "RANK" not in os.environ                  # plain `python`: ONE engine over every GPU of the process
 if INPROC:
-    rank, world, local = 0, torch.cuda.device_count(), 0
-    eng = pkg.Engine(list(range(world)))
+    devices = [int(d) for d in os.environ["MCB_STRESS_DEVICES"].split(",")] if os.environ.get("MCB_STRESS_DEVICES") \
+        else list(range(torch.cuda.device_count()))        # e.g. MCB_STRESS_DEVICES=0,0,0: three shards on one GPU
+    rank, world, local = 0, len(devices), 0
+    eng = pkg.Engine(devices)
     solo = pkg.Engine(0)
 else:
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
@@ -51,7 +53,7 @@ flag = torch.tensor([bad, eng.peer_timeouts()], dtype=torch.int64, device="cuda"
 if not INPROC:
     dist.all_reduce(flag)
 if rank == 0:
-    shape = "one engine over %d GPUs" % world if INPROC else "%d ranks" % world
+    shape = "one engine over %d shards" % world if INPROC else "%d ranks" % world
     print(f"stress: {jobs} jobs on {shape}, mismatches {int(flag[0])}, timeouts {int(flag[1])}")
 eng.close()
 solo.close()
