@@ -181,6 +181,9 @@ struct mcb_engine {
     unsigned long long last_job_epoch = 0; // mcb_last_segments: the last collected European job ...
     uint64_t last_job_chunks = 0;          // ... and its chunk count (0: the last whole job left h_segments instead)
     uint64_t ring_chunks[kHostRing] = {};  // chunk count of the job in each host slot
+    bool ring_own[kHostRing] = {};         // ... and whether it was priced as a group of one (segments in mailbox->own)
+    bool last_job_own = false;
+    unsigned long long slot_last_sharded[kRing] = {};   // separate processes: last sharded job per mailbox slot (acks)
     int rank = 0, world = 1;               // this shard's place in its group
     bool in_process = false;               // group = the shards of ONE multi-device engine (events, no device spins)
     bool ipc = false;                      // group = one engine per process, mailboxes mapped over CUDA IPC
@@ -787,6 +790,7 @@ int mcb_peer_mailbox_connect(mcb_engine *e, int rank, int world, const void *all
     std::vector<unsigned long long> acks(kMaxPeers, (unsigned long long)base_epoch);
     CU(cudaMemcpy(e->mailbox->consumed, acks.data(), sizeof(unsigned long long) * kMaxPeers, cudaMemcpyHostToDevice));
     e->job_epoch = base_epoch;
+    for (int k = 0; k < kRing; ++k) e->slot_last_sharded[k] = 0;   // (the acks were just reset to base_epoch)
     e->rank = rank;
     e->world = world;
     e->ipc = world > 1;
@@ -886,7 +890,11 @@ int submit_shard(mcb_engine *s, mcb_engine *L, const mcb_option_data *opt, uint6
     args.rank = rank;
     args.world = world;
     args.n_consumers = (s->ipc && !solo) ? world : 1;
-    args.check_acks = (s->ipc && !solo) ? 1 : 0;
+    if (s->ipc && !solo) {
+        args.ack_epoch = s->slot_last_sharded[slot];
+        s->slot_last_sharded[slot] = epoch;
+    }
+    if (solo) args.peers.box[0] = s->mailbox;
     if (world == 1) {
         args.d_out = s->results.ptr;
         args.h_out = &s->h_ring[epoch % kHostRing];
@@ -898,7 +906,7 @@ int submit_shard(mcb_engine *s, mcb_engine *L, const mcb_option_data *opt, uint6
                                                                st)))
             return rc;
         segments_job_kernel<<<(unsigned)(seg_hi - seg_lo), kSlots, 0, st>>>(args, partials.ptr, c_lo);
-    } else if (c_hi > c_lo && n_chunks <= kSmallJobChunks && s->small_jobs) {
+    } else if (c_hi > c_lo && n_chunks <= kSmallJobChunks && s->small_jobs && world == 1) {
         // small job: a cluster of eight CTAs per chunk (latency, see european_small_job_kernel)
         const EuropeanParams prm = european_params(opt, opt->K, opt->v, n_paths, seed, c_lo);
         TimedScope timed(s, MCB_KERNEL_EUROPEAN, st);
@@ -922,9 +930,6 @@ int submit_shard(mcb_engine *s, mcb_engine *L, const mcb_option_data *opt, uint6
     s->launches++;
     CU(cudaGetLastError());
     if (world > 1) CU(cudaEventRecord(s->p_done[slot], st));
-    // a solo job used the leader's mailbox slot: the producers of job epoch + kRing wait for this event as they
-    // would for the final pass of a sharded job
-    if (solo) CU(cudaEventRecord(L->f_done[slot], st));
     return MCB_OK;
 }
 
@@ -951,10 +956,14 @@ int mcb_european_submit(mcb_engine *e, const mcb_option_data *opt, uint64_t n_pa
     e->ring_chunks[epoch % kHostRing] = (n_paths + kEuropeanChunk - 1) / kEuropeanChunk;
     std::atomic_thread_fence(std::memory_order_seq_cst);
     const size_t n = shard_count(e);
-    // A small job on an in-process group is not worth sharding (a 10^5-path call is 10 us on one GPU, 30-40 us once
-    // launcher threads, cross-device events and a final pass are involved): the leader prices it alone, same bits.
-    if (n > 1 && e->in_process && e->small_jobs && e->ring_chunks[epoch % kHostRing] <= kSmallJobChunks)
-        return submit_shard(e, e, opt, n_paths, seed, option_type, epoch, true);
+    // A small job is not worth sharding (a 10^5-path call is 10 us on one GPU, 30-40 us once launcher threads,
+    // cross-device events or peer flags and a final pass are involved): the leader of an in-process group -- every
+    // rank of a group of processes -- prices it alone as a group of one.  Same tree, same bits; it touches no
+    // mailbox slot a peer writes, and the epoch advances on every rank as for any other job.
+    const bool small = e->small_jobs && e->ring_chunks[epoch % kHostRing] <= kSmallJobChunks;
+    const bool solo = small && ((n > 1 && e->in_process) || e->ipc);
+    e->ring_own[epoch % kHostRing] = small && (solo || e->world == 1);
+    if (solo) return submit_shard(e, e, opt, n_paths, seed, option_type, epoch, true);
     // the other shards' launcher threads enqueue their devices while this thread does the leader's
     for (size_t i = 1; i < n; ++i) {
         mcb_engine *s = shard_at(e, i);
@@ -996,7 +1005,7 @@ int mcb_european_collect(mcb_engine *e, uint64_t ticket, mcb_result *out)
         return fail(MCB_ERR_INVALID, "ticket %llu has expired (only the last %d results are kept)",
                     (unsigned long long)ticket, kHostRing);
     volatile HostSlot *hs = &e->h_ring[ticket % kHostRing];
-    // The result arrives in mapped host memory straight from the kernel: spin on its sequence word
+    // The result arrives in mapped host memory straight from the kernel: spin until its ten tagged words are there
     // (no cudaStreamSynchronize round trip); every so often make sure the streams are still healthy.
     const auto t0 = std::chrono::steady_clock::now();
     unsigned long long spins = 0;
@@ -1034,6 +1043,7 @@ int mcb_european_collect(mcb_engine *e, uint64_t ticket, mcb_result *out)
     memcpy(out, &got, sizeof(mcb_result));
     e->last_job_epoch = ticket;
     e->last_job_chunks = e->ring_chunks[ticket % kHostRing];
+    e->last_job_own = e->ring_own[ticket % kHostRing];
     if (out->n_paths == 0 || out->price != out->price)
         return fail(MCB_ERR_TIMEOUT, "ticket %llu: a peer did not deliver its segments within %.1f s (result poisoned)",
                     (unsigned long long)ticket, (double)e->timeout_ns * 1e-9);
@@ -2072,8 +2082,8 @@ int mcb_last_segments(mcb_engine *e, double *segments)
     if (e->job_epoch - e->last_job_epoch >= (unsigned long long)kRing)
         return fail(MCB_ERR_INVALID, "the segments of the last collected job have been overwritten");
     DeviceGuard g(e->device);
-    CU(cudaMemcpy(segments, e->mailbox->gather[e->last_job_epoch % kRing], sizeof(double) * 2 * MCB_SEGMENTS,
-                  cudaMemcpyDeviceToHost));
+    const double *src = e->last_job_own ? e->mailbox->own[e->last_job_epoch % kRing] : e->mailbox->gather[e->last_job_epoch % kRing];
+    CU(cudaMemcpy(segments, src, sizeof(double) * 2 * MCB_SEGMENTS, cudaMemcpyDeviceToHost));
     for (int sg = 0; sg < MCB_SEGMENTS; ++sg)   // segments without a chunk are +0.0 by rule (never stored)
         if ((e->last_job_chunks * (uint64_t)sg) / MCB_SEGMENTS == (e->last_job_chunks * (uint64_t)(sg + 1)) / MCB_SEGMENTS)
             segments[2 * sg] = segments[2 * sg + 1] = 0.0;

@@ -613,8 +613,9 @@ struct PeerMailbox {           // one per shard, in that shard's HBM; written by
     unsigned long long consumed[kMaxPeers];            // consumed[c] = last epoch consumer c folded (its ack to ME)
     unsigned int timeouts;                             // bounded waits that ran out (sticky, diagnostic)
     // small one-GPU jobs: the segments as self-tagged words (low half | tag << 32, high half | tag << 32 of sum and
-    // sumsq), so that no fence and no ticket stand between a chunk's totals and the final tree (small_job_tail)
+    // sumsq), so that no fence and no ticket stand between a chunk's totals and the final tree (small_job_tail_one_gpu)
     alignas(32) unsigned long long tagged[kRing][kSegments][4];   // (read with 16-byte loads)
+    double own[kRing][kSegments * 2];                  // ... and in the clear for mcb_last_segments; no peer writes here
 };
 struct PeerTable {
     PeerMailbox *box[kMaxPeers];                       // box[r] = shard r's mailbox as mapped here
@@ -658,7 +659,8 @@ struct JobArgs {
     int live_segments;              // ... of which have at least one chunk
     int rank, world;
     int n_consumers;                // shards [0, n_consumers) receive the segments (world: all-gather; 1: gather)
-    int check_acks;                 // producers wait for the consumers' acks of job epoch - kRing (separate processes)
+    unsigned long long ack_epoch;   // separate processes: the last SHARDED job that used this mailbox slot; producers wait
+                                    // until every consumer has acknowledged it (0: nothing to wait for)
 };
 
 __device__ __forceinline__ unsigned long long global_timer_ns()
@@ -740,9 +742,8 @@ __device__ __forceinline__ void job_publish_segment(const JobArgs &args, int seg
     PeerMailbox *mine = args.peers.box[args.rank];
     if (threadIdx.x == 0) {
         for (int c = 0; c < args.n_consumers; ++c) {
-            // the slot still holds job epoch - kRing until consumer c has folded it
-            if (args.check_acks && args.epoch > (unsigned long long)kRing &&
-                !wait_at_least(&mine->consumed[c], args.epoch - kRing, args.timeout_ns)) {
+            // the slot still holds its previous sharded job until consumer c has folded it
+            if (args.ack_epoch && !wait_at_least(&mine->consumed[c], args.ack_epoch, args.timeout_ns)) {
                 atomicAdd(&mine->timeouts, 1u);
                 continue;                                   // c will time out on this job and report NaN
             }
@@ -939,41 +940,6 @@ __device__ __forceinline__ void cluster_store_signal2(uint32_t addr, float v, fl
                  : "memory");
 }
 
-// Warp-level tail of european_small_job_kernel in a group of several shards (warp 0 of the cluster's CTA 0; lane 0 holds
-// the chunk's totals): store the segment into every consumer's mailbox slot, take the shard ticket, and in the shard's
-// last chunk publish the flag -- job_publish_segment without block barriers.
-__device__ __forceinline__ void small_job_tail(const JobArgs &args, float2 *__restrict__ partials, uint64_t chunk,
-                                               uint64_t first_chunk, float sum, float sq, int lane)
-{
-    const int slot = (int)(args.epoch % (unsigned long long)kRing);
-    PeerMailbox *mine = args.peers.box[args.rank];
-    const uint32_t n = (uint32_t)args.n_chunks;
-    const double a = (double)sum, b = (double)sq;     // a one-chunk segment IS its partial (see job_tail)
-    int last = 1;
-    if (lane == 0) {
-        partials[chunk - first_chunk] = make_float2(sum, sq);
-        const uint32_t seg = (kSegments * ((uint32_t)chunk + 1u) + n - 1u) / n - 1u;   // n <= kSegments
-        for (int c = 0; c < args.n_consumers; ++c) {
-            if (args.check_acks && args.epoch > (unsigned long long)kRing &&
-                !wait_at_least(&mine->consumed[c], args.epoch - kRing, args.timeout_ns)) {
-                atomicAdd(&mine->timeouts, 1u);
-                continue;
-            }
-            double *dst = args.peers.box[c]->gather[slot] + 2 * seg;
-            __stcg(dst, a);
-            __stcg(dst + 1, b);
-        }
-        __threadfence_system();
-        last = atomicAdd(&args.seg_tickets[kSegments], 1u) == (unsigned int)args.live_segments - 1u ? 1 : 0;
-        if (last) args.seg_tickets[kSegments] = 0u;   // ready for the next launch
-    }
-    last = __shfl_sync(kFullMask, last, 0);
-    if (!last) return;
-    __threadfence_system();
-    if (lane < args.n_consumers)
-        *((volatile unsigned long long *)&args.peers.box[lane]->flags[slot][args.rank]) = args.epoch;
-}
-
 // Spin (bounded) until the tagged words of this lane's two segments (each only if `want`ed) carry `tag`; the loads of
 // both segments are in flight together, so the usual case costs one L2 round trip.  Returns the doubles they spell.
 __device__ __forceinline__ bool read_tagged_pair(const unsigned long long *lo, const unsigned long long *hi, bool want_lo,
@@ -1009,12 +975,14 @@ __device__ __forceinline__ bool read_tagged_pair(const unsigned long long *lo, c
     return true;
 }
 
-// world == 1 version of the tail.  One chunk: the tree runs on registers.  2..64 chunks: every chunk's lane 0 stores
+// Warp-level tail of european_small_job_kernel (warp 0 of the cluster's CTA 0; lane 0 holds the chunk's totals), for a
+// group of one.  One chunk: the tree runs on registers.  2..64 chunks: every chunk's lane 0 stores
 // its segment as four self-tagged 8-byte words and leaves; warp 0 of chunk 0 -- the first cluster to be scheduled,
 // so it is waiting while the others still price -- reads the live segments until their tags match (bounded by the
 // engine's timeout; the other chunks wait for nobody, so they always get their SMs) and runs the tree.  Neither a
 // fence nor an atomic round trip is left on the path from the last payoff to the result (they cost 2 400 + 1 100
-// clk, tools/job_latency_probe.cu); the plain copy in `gather` serves mcb_last_segments.
+// clk, tools/job_latency_probe.cu); the plain copy in `own` serves mcb_last_segments.  Nothing a peer may write is touched,
+// so a shard of a larger group can price such a job by itself (args.world == 1, box[0] = its own mailbox).
 __device__ __forceinline__ void small_job_tail_one_gpu(const JobArgs &args, float2 *__restrict__ partials, uint64_t chunk,
                                                        float sum, float sq, int lane)
 {
@@ -1026,7 +994,7 @@ __device__ __forceinline__ void small_job_tail_one_gpu(const JobArgs &args, floa
     if (lane == 0) {
         partials[chunk] = make_float2(sum, sq);
         const uint32_t seg = (kSegments * ((uint32_t)chunk + 1u) + n - 1u) / n - 1u;   // n <= kSegments
-        double *dst = mine->gather[slot] + 2 * seg;
+        double *dst = mine->own[slot] + 2 * seg;
         dst[0] = a;
         dst[1] = b;
         if (n > 1) {
@@ -1147,8 +1115,7 @@ european_small_job_kernel(const __grid_constant__ EuropeanParams prm, const __gr
         y = y + __shfl_down_sync(kFullMask, y, off);
     }
     MCB_TRACE(2)
-    if (args.world == 1) small_job_tail_one_gpu(args, partials, chunk, x, y, lane);
-    else small_job_tail(args, partials, chunk, prm.first_chunk, x, y, lane);
+    small_job_tail_one_gpu(args, partials, chunk, x, y, lane);   // (the engine launches this kernel for groups of one only)
 }
 
 // A shard that owns no chunk of a (small) job still owes its consumers its flag (its segments are

@@ -66,8 +66,19 @@ def _worker(rank, world, port, out_dir):
                 rp = peer.price_european(opt, n_big + k, 1234, pkg.CALL)
                 assert eng2.launch_count - before == 2, "one pricing launch + one final pass per job"
                 peer_out += [rp.sum, rp.sumsq, rp.price, float(rp.n_paths)]
-            small = peer.price_european(opt, 100_000, 1234, pkg.PUT)   # 7 chunks: most ranks own none
+            before = eng2.launch_count
+            small = peer.price_european(opt, 100_000, 1234, pkg.PUT)   # <= 64 chunks: every rank prices it alone
+            assert eng2.launch_count - before == 1, "a small job is one launch on every rank, no final pass"
             peer_out += [small.sum, small.sumsq, small.price, float(small.n_paths)]
+            # small (unsharded) and sharded jobs interleaved and pipelined: a sharded job whose mailbox slot was last
+            # used by a sharded job many epochs ago, after runs of small ones, must not wait for acks nobody sends
+            mixed = [1, 100_000, 64 * pkg.EUROPEAN_CHUNK, 5 * pkg.EUROPEAN_CHUNK + 3, 16_384, n_big + 20, 7, 2 * pkg.EUROPEAN_CHUNK,
+                     33, n_big + 21, n_big + 22, 999, n_big + 23]
+            for lo in range(0, len(mixed), pkg.PIPELINE_DEPTH):
+                tk = [eng2.european_submit(opt, m, 1234, pkg.CALL) for m in mixed[lo:lo + pkg.PIPELINE_DEPTH]]
+                for t in tk:
+                    rp = eng2.european_collect(t)
+                    peer_out += [rp.sum, rp.sumsq, float(rp.n_paths)]
             # pipelined: several jobs in flight, collected afterwards
             tickets = [eng2.european_submit(opt, n_big + 10 + k, 1234, pkg.CALL) for k in range(6)]
             for t in tickets:
@@ -115,6 +126,10 @@ def test_nccl_sharded_prices_match_single_gpu_bits(tmp_path, pkg, engine):
             want_peer += [r1.sum, r1.sumsq, r1.price, float(n_big + k)]
         r2 = engine.price_european(pkg.option(), 100_000, 1234, pkg.PUT)
         want_peer += [r2.sum, r2.sumsq, r2.price, 100_000.0]
+        for m in [1, 100_000, 64 * pkg.EUROPEAN_CHUNK, 5 * pkg.EUROPEAN_CHUNK + 3, 16_384, n_big + 20, 7, 2 * pkg.EUROPEAN_CHUNK,
+                  33, n_big + 21, n_big + 22, 999, n_big + 23]:
+            rm = engine.price_european(pkg.option(), m, 1234, pkg.CALL)
+            want_peer += [rm.sum, rm.sumsq, float(m)]
         for k in range(6):
             r3 = engine.price_european(pkg.option(), n_big + 10 + k, 1234, pkg.CALL)
             want_peer += [r3.sum, r3.sumsq]

@@ -243,6 +243,9 @@ def test_a_missing_peer_poisons_the_result_instead_of_inventing_one(pkg, engine)
             eng.european_collect(ticket)
         assert ei.value.status == pkg.ERR_TIMEOUT
         assert eng.peer_timeouts() >= 1
+        # a small job needs no peer (every rank prices it alone): it still comes out right in the broken group
+        lone = eng.price_european(pkg.option(), 100_000, 1234, pkg.PUT)
+        assert _bits(lone) == _bits(engine.price_european(pkg.option(), 100_000, 1234, pkg.PUT))
         # back to a group of one: same engine, same bits as ever
         eng.peer_mailbox_connect(0, 1, [mine], eng.peer_epoch())
         got = eng.price_european(pkg.option(), n, 1234, pkg.CALL)
