@@ -14,19 +14,24 @@ __device__ unsigned long long g_cta[4][512];   // [stamp][CTA]: entry, payoffs s
     }
 #include "../monte-carlo-project-cuda_b200/csrc/mcb200.cu"
 
-int main()
+int main(int argc, char **argv)
 {
     mcb_engine *e = nullptr;
     if (mcb_engine_create(0, &e)) { printf("%s\n", mcb_last_error()); return 1; }
     mcb_option_data opt{};
     opt.S0 = 100.f; opt.K = 100.f; opt.T = 1.f; opt.r = 0.1f; opt.v = 0.2f; opt.B = 0.f; opt.P1 = 0; opt.P2 = 0; opt.N_PATHS = 0; opt.N_STEPS = 1;
-    const unsigned long long sizes[5] = {1ull, 16384ull, 100000ull, 1000000ull, 2000000ull};
+    unsigned long long sizes[16] = {1ull, 16384ull, 100000ull, 1000000ull, 2000000ull};   // or the sizes on the command line
+    int n_sizes = 5;
+    if (argc > 1) {
+        n_sizes = argc - 1 > 16 ? 16 : argc - 1;
+        for (int i = 0; i < n_sizes; ++i) sizes[i] = strtoull(argv[i + 1], nullptr, 10);
+    }
     // small jobs (european_small_job_kernel): 1 = pricing + first cluster barrier, 2 = slot sums + fold + second barrier
     const char *names[10] = {"entry", "pricing", "fold", "segment ticket", "shard ticket", "tree loads+fold", "fp64 stats",
                              "result stores", "", ""};
     int clk_khz = 0;
     cudaDeviceGetAttribute(&clk_khz, cudaDevAttrClockRate, 0);
-    for (int k = 0; k < 5; ++k) {
+    for (int k = 0; k < n_sizes; ++k) {
         mcb_result r;
         const int reps = 3000;
         for (int i = 0; i < 300; ++i) mcb_price_european(e, &opt, sizes[k], 1234, MCB_CALL, &r);
