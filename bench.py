@@ -616,7 +616,7 @@ def other_workloads(torch, pkg, eng, hbm_gbs, peak_src):
         torch.cuda.synchronize()
         return a.elapsed_time(b) * 1e-3 / reps
 
-    # configs[0]: 1e6 paths (and hello.cu's own 1e5, hello.cu:13) through the synchronous public call
+    # configs[0]: 1e6 paths (and hello.cu's own 1e5, hello.cu:14) through the synchronous public call
     # (host in / host out): call latency.  ONE launch, result through mapped pinned memory.
     for label, npaths in (("european_1e6_sync_call", 1_000_000), ("european_1e5_sync_call_hello_cu_size", 100_000)):
         o0 = pkg.option(N_PATHS=npaths, **CFG)

@@ -66,7 +66,7 @@ int main(int argc, char **argv)
     rc |= mcb_nested_monte_carlo(engine, &nm, 0, 10, 1234, 1235, MCB_DISCOUNT_CORRECT, F, NULL, NULL, MCB_HOST, &mean_F);
     printf("C_MORE %d %.17g %.17g %.17g %.9g %.9g %.17g\n", rc, sweep[0].sum, sweep[1].sum, sweep[2].sum, (double)F[0],
            (double)F[119], mean_F);
-    /* latency of the synchronous call, from the reference's own job size (hello.cu:13: 1e5 paths) down to
+    /* latency of the synchronous call, from the reference's own job size (hello.cu:14: 1e5 paths) down to
      * one path (pure call overhead: launch + ticket + final tree + host-visible result) */
     {
         const uint64_t sizes[6] = {1, 16384, 100000, 1000000, 16384, 1};   /* (the small ones twice: first and last) */

@@ -879,7 +879,7 @@ european_job_kernel(const __grid_constant__ EuropeanParams prm, const __grid_con
 }
 
 // ------------------------------------------------------------------------------------------
-// SMALL jobs (at most kSegments chunks = 1 048 576 paths: the reference's own call sizes, hello.cu:26 / testing.cu).
+// SMALL jobs (at most kSegments chunks = 1 048 576 paths: the reference's own call sizes, hello.cu:14,31 / testing.cu).
 // A synchronous call of that size is latency, not throughput: one CTA alone needs 13 750 clk (7 us) for the 64 serial
 // path evaluations of its 256 slots (tools/job_latency_probe.cu).  Here a CLUSTER of eight CTAs on eight SMs prices one
 // chunk: CTA r evaluates paths [8r, 8r + 8) of every slot (eight independent Philox chains per thread) and sends each
