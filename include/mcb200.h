@@ -219,6 +219,10 @@ int mcb_nested_async(mcb_engine *e, const mcb_option_data *opt, uint64_t first_o
  * waits for the flags (bounded, see mcb_set_wait_timeout_ms), so the pricing stream never waits for a
  * peer: job e + 1 is priced while job e's segments are still crossing NVLink.  Up to
  * MCB_PIPELINE_DEPTH jobs may be in flight; the last MCB_RESULT_RING results can be collected.
+ * A job of at most 2^20 paths (the reference's own call sizes, hello.cu:14) is latency-bound and is NOT
+ * sharded: the leader of a multi-device engine / every rank of a process group prices it alone, with a
+ * cluster of eight CTAs per 16384-path chunk (10-14 us per synchronous call; the tree is the same, so are
+ * the bits).
  * Results are bit-identical for every group shape.  Every rank of a process group must submit the
  * same jobs in the same order.  If a peer never delivers, collect returns MCB_ERR_TIMEOUT and the
  * result is NaN with n_paths = 0 (never a plausible number). */

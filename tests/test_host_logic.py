@@ -165,3 +165,42 @@ def test_python_constants_match_the_header(pkg):
         assert enum(name) == value, name
     assert pkg.Result.__dict__ is not None and __import__("ctypes").sizeof(pkg.Result) == 40
     assert __import__("ctypes").sizeof(pkg.OptionData) == 48
+
+
+def test_small_job_segment_closed_form():
+    """european_small_job_kernel (pricing_kernels.cuh, small_job_tail_one_gpu) finds the segment of chunk c of an
+    n-chunk job, n <= 64, as (64 (c + 1) + n - 1) / n - 1 in 32-bit arithmetic instead of searching the segment
+    bounds floor(n s / 64) <= c < floor(n (s + 1) / 64) the other kernels and the oracle use: same answer for
+    every (n, c), every such segment holds exactly that one chunk, and a one-chunk job lives in segment 63."""
+    for n in range(1, 65):
+        owners = {}
+        for s in range(64):
+            for c in range((n * s) // 64, (n * (s + 1)) // 64):
+                assert c not in owners
+                owners[c] = s
+        assert sorted(owners) == list(range(n))
+        for c in range(n):
+            assert (64 * (c + 1) + n - 1) // n - 1 == owners[c], (n, c)
+            assert (n * (owners[c] + 1)) // 64 - (n * owners[c]) // 64 == 1
+    assert (64 * 1 + 1 - 1) // 1 - 1 == 63
+
+
+def test_result_slot_words_round_trip():
+    """The flag-in-data result slot (HostSlot, pricing_kernels.cuh / host_slot_read, mcb200.cu): five 8-byte fields travel
+    as ten (half | tag << 32) words; a slot is complete only when all ten carry the ticket's tag, and the value an
+    expired slot holds can never match it."""
+    import struct
+    fields = [struct.unpack("<Q", struct.pack("<d", x))[0] for x in (10.45, 0.0143, 1.1e10, float("nan"))] + [1 << 40]
+    for ticket in (1, 7, 0xffffffff, 1 << 32, (1 << 32) + 5):
+        tag = ticket & 0xffffffff
+        words = []
+        for f in fields:
+            words += [(tag << 32) | (f & 0xffffffff), (tag << 32) | (f >> 32)]
+        never = ((~ticket) & 0xffffffff) << 32
+        assert all((never >> 32) != (w >> 32) for w in words)
+        for missing in range(10):                          # any word still expired: not complete
+            partial = list(words)
+            partial[missing] = never
+            assert not all((w >> 32) == tag for w in partial)
+        back = [(words[2 * k] & 0xffffffff) | ((words[2 * k + 1] & 0xffffffff) << 32) for k in range(5)]
+        assert back == fields
